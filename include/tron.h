@@ -1,0 +1,182 @@
+/*
+ * tron.h -- C ABI of libtron_b200: a B200-native (sm_100a) radial NUFFT engine
+ * that is a drop-in for the hot path of davidssmith/TRON.
+ *
+ * Two layers are exported, both extern "C", plain pointers and sizes only:
+ *
+ *  1. The plan API (new).  The reference keeps its geometry in file-static
+ *     globals that only main() sets (/root/reference/src/tron.cu:54-87,
+ *     905-961), so its host entry points are not independently callable.
+ *     A tron_config carries exactly what main() derives from the RA header and
+ *     the command line; tron_plan_create() derives the geometry with the same
+ *     integer truncations and owns every device buffer, table and stream.
+ *
+ *  2. The legacy symbols of the reference (tron.h:55-72, tron.cu:460-788):
+ *     recon_radial2d / recon_radial_2d, tron_init, tron_shutdown,
+ *     tron_nufft_adj_radial2d, tron_nufft_radial2d, and the two
+ *     `extern "C" __global__` kernels gridradial2d / degridradial2d (kept as
+ *     launch-configuration-agnostic compatibility shims, see tron_b200/csrc/
+ *     legacy.cu).  They read a process-global configuration installed with
+ *     tron_set_config(), the replacement for main()'s writes to the globals.
+ *
+ * Data layout at this boundary is the reference's: complex64 (or complex-half
+ * when fp16 storage is selected), channel fastest, i.e. RA dims
+ * [nc, nt, nro, npe1, npe2] column-major:
+ *     samples[nc*(nro*pe + ro) + ch],   image[nx*row + col]   (adjoint output)
+ *     image  [nc*(nx*row + col) + ch],  samples as above       (forward)
+ *
+ * Errors: every int-returning function returns 0 on success and a negative
+ * TRON_E* code otherwise; tron_last_error() holds the message.  Nothing in
+ * this library calls exit() or blocks on stdin (the reference does both,
+ * tron.cu:92-100,138-147).  There is no CPU fallback: without a CUDA device
+ * tron_plan_create() fails with TRON_ENODEV.
+ */
+#ifndef TRON_B200_TRON_H
+#define TRON_B200_TRON_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ra.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRON_B200_VERSION 100
+
+enum {
+    TRON_OK = 0,
+    TRON_EINVAL = -1,      /* bad configuration (e.g. odd nc != 1, nt != 1, nxos % 4) */
+    TRON_ENODEV = -2,      /* no usable CUDA device */
+    TRON_ECUDA = -3,       /* a CUDA runtime call failed */
+    TRON_ENOMEM = -4,
+    TRON_EUNSUPPORTED = -5 /* valid in the reference's CLI but not implemented (-3, -i) */
+};
+
+/* What main() reads from the RA header and getopt (tron.cu:822-874, 905-961). */
+typedef struct tron_config {
+    uint64_t dims[5];       /* input RA dims */
+    int   adjoint;          /* -a */
+    int   golden_angle;     /* -G */
+    float gridos;           /* -o  (default 2) */
+    float kernwidth;        /* -k  (default 2) */
+    float data_undersamp;   /* -u  (default 1) */
+    int   prof_slide;       /* -d  (default 0 = npe1work) */
+    int   skip_angles;      /* -s */
+    int   niter;            /* -i  (CGNR; must be 0) */
+    int   koosh;            /* -3  (must be 0: the reference has no 3-D kernels) */
+    int   verbose;          /* -v */
+    int   device;           /* -g  (-1 = leave the current device alone) */
+    /* ---- extensions (all 0 = reference behaviour) ---- */
+    int   half_in;          /* input payload is complex-half (fp16 storage) */
+    int   half_out;         /* output payload is complex-half */
+    int   slice_begin;      /* adjoint: this plan reconstructs slices [slice_begin, slice_end) */
+    int   slice_end;        /*          0,0 = all nz slices */
+    int   coil_begin;       /* this plan owns channels [coil_begin, coil_end) of the nc in dims[0] */
+    int   coil_end;         /*          0,0 = all */
+    int   sos_partial;      /* adjoint, nc>1: emit sum |z_c|^2 as float32[nx*ny] per slice (no sqrt),
+                               for a cross-GPU sum when coils are sharded */
+    int   batch_slices;     /* slices per kernel launch, 0 = auto */
+    int   per_coil_out;     /* adjoint: skip the coil combine, emit [nx*ny*nc] per slice
+                               (what tron_nufft_adj_radial2d returns in the reference) */
+} tron_config;
+
+/* Derived geometry, same names as the reference's globals (tron.cu:76-79). */
+typedef struct tron_geometry {
+    int nc, nt, nro, npe1, npe2, npe1work;
+    int nx, ny, nz, nxos, nyos;
+    int prof_slide;
+    int slice_begin, slice_end;       /* resolved shard */
+    int coil_begin, coil_end;
+    uint64_t out_dims[5];             /* RA dims of the full output (dims[0] = 1 as in tron.cu:899) */
+    uint64_t in_elems;                /* complex elements of the full input */
+    uint64_t out_elems;               /* complex elements of the full output */
+    uint64_t shard_in_offset;         /* first input element this plan reads (full-array index) */
+    uint64_t shard_in_elems;          /* contiguous input elements this plan reads */
+    uint64_t shard_out_offset;        /* first output element this plan writes */
+    uint64_t shard_out_elems;
+} tron_geometry;
+
+typedef struct tron_plan tron_plan;
+
+void tron_config_defaults(tron_config *cfg);
+/* host-only: works without a GPU */
+int  tron_geometry_compute(const tron_config *cfg, tron_geometry *g);
+
+int  tron_plan_create(tron_plan **plan, const tron_config *cfg);
+int  tron_plan_destroy(tron_plan *plan);
+int  tron_plan_geometry(const tron_plan *plan, tron_geometry *g);
+
+/* Whole job on HOST buffers: H2D, kernels, D2H; returns when h_out is complete.
+ * h_in / h_out point at the plan's shard (element shard_in_offset /
+ * shard_out_offset of the full arrays).  Replaces recon_radial2d's span
+ * (tron.cu:726-786) without its per-call plan/buffer creation. */
+int  tron_recon_host(tron_plan *plan, void *h_out, const void *h_in);
+
+/* Whole job on DEVICE-resident buffers, asynchronous on `stream`
+ * (a cudaStream_t; NULL = the CUDA default stream, as everywhere in CUDA). */
+int  tron_recon_device(tron_plan *plan, void *d_out, const void *d_in, void *stream);
+
+/* Stage-level entry points (parity tests, profiling, roofline timing).
+ * tron_grid_device: adjoint interpolation only (density compensation and the
+ *   1/(nxos*npe) scale folded in) for `nslices` slices starting at shard-local
+ *   slice z0; d_grid receives nslices*nc planes of nxos*nxos complex64, planar
+ *   ([slice][ch][row][col]).  Replaces precompensate + gridradial2d
+ *   (tron.cu:405-416, 465-536).
+ * tron_grid_to_interleaved: planar -> the reference's [row][col][ch] order.
+ * tron_degrid_device: forward interpolation of one oversampled grid in the
+ *   reference's channel-interleaved order -> samples (tron.cu:540-577). */
+int  tron_grid_device(tron_plan *plan, void *d_grid, const void *d_samples, int z0, int nslices, void *stream);
+int  tron_grid_to_interleaved(tron_plan *plan, void *d_dst, const void *d_grid, int nslices, void *stream);
+int  tron_degrid_device(tron_plan *plan, void *d_samples, const void *d_grid, void *stream);
+/* average device milliseconds of the last tron_recon_* call's stages:
+ * ms[0] = gridding/degridding kernels, ms[1] = FFT passes, ms[2] = everything else on the stream */
+int  tron_plan_last_stage_ms(tron_plan *plan, float ms[3]);
+/* number of kernel launches issued by the last tron_recon_* call */
+int  tron_plan_last_launches(const tron_plan *plan);
+
+const char *tron_last_error(void);
+int  tron_version(void);
+
+/* ------------------------------------------------------------------ */
+/* Legacy surface of the reference (tron.h:55-72, tron.cu:579-786)     */
+/* ------------------------------------------------------------------ */
+#if defined(__CUDACC__) || defined(__VECTOR_TYPES_H__)
+typedef float2 tron_float2;
+#else
+typedef struct { float x, y; } tron_float2;
+#endif
+
+/* replaces main()'s assignment of the file-static globals */
+int  tron_set_config(const tron_config *cfg);
+void tron_init(void);                                                     /* tron.cu:579 */
+void tron_shutdown(void);                                                 /* tron.cu:608 */
+void tron_nufft_adj_radial2d(tron_float2 *d_out, tron_float2 *d_in, const int j);   /* tron.cu:623 */
+void tron_nufft_radial2d(tron_float2 *d_out, tron_float2 *d_in, const int j);       /* tron.cu:639 */
+void recon_radial2d(tron_float2 *h_outdata, const tron_float2 *h_indata);           /* tron.cu:726 */
+void recon_radial_2d(tron_float2 *h_outdata, const tron_float2 *h_indata);          /* tron.h:71 spelling */
+
+/* host launchers for the two compatibility kernels below (FFI users have no <<<>>>) */
+int  tron_launch_gridradial2d(void *udata, const void *nudata, int nxos, int nchan, int nro, int npe,
+                              float kernwidth, float gridos, int skip_angles, int golden,
+                              int blocks, int threads, void *stream);
+int  tron_launch_degridradial2d(void *nudata, const void *udata, int n, int nrep, int nro, int npe,
+                                float W, float gridos, int skip_angles, int golden,
+                                int blocks, int threads, void *stream);
+
+#ifdef __CUDACC__
+/* Compatibility kernels with the reference's exact parameter lists (tron.h:58-67).
+ * Correct for any <<<blocks, threads>>>. */
+__global__ void gridradial2d(float2 *udata, const float2 *__restrict__ nudata, const int ngrid,
+                             const int nchan, const int nro, const int npe, const float kernwidth,
+                             const float grid_oversamp, const int skip_angles, const int flag_golden_angle);
+__global__ void degridradial2d(float2 *nudata, const float2 *__restrict__ udata, const int nimg,
+                               const int nchan, const int nro, const int npe, const float kernwidth,
+                               const float gridos, const int skip_angles, const int flag_golden_angle);
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRON_B200_TRON_H */

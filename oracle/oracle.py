@@ -72,6 +72,8 @@ class Oracle:
         L.oracle_halfbits_to_floatbits.restype = C.c_uint32
         L.oracle_halfbits_to_floatbits.argtypes = [C.c_uint16]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_trig_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._trig = None
 
     # -- configuration ----------------------------------------------------
     def config(self, dims, adjoint, golden=False, gridos=2.0, kernwidth=2.0, undersamp=1.0,
@@ -95,6 +97,16 @@ class Oracle:
         if rc:
             raise ValueError("oracle_recon_radial2d failed (%d)" % rc)
         return out
+
+    def set_trig_table(self, ct=None, st=None):
+        """Install SFU sin/cos values of the spokes (index pe+skip for golden, pe for linear); None clears."""
+        if ct is None:
+            self._trig = None
+            self.lib.oracle_set_trig_table(None, None, 0)
+            return
+        ct = np.ascontiguousarray(ct, dtype=np.float32); st = np.ascontiguousarray(st, dtype=np.float32)
+        self._trig = (ct, st)                       # keep alive
+        self.lib.oracle_set_trig_table(_ptr(ct), _ptr(st), int(ct.size))
 
     # -- kernels -----------------------------------------------------------
     def grid(self, samples, nxos, nchan, nro, npe, W=2.0, skip=0, golden=False):
@@ -189,6 +201,7 @@ class RefLib:
         L.tronref_host_alloc.restype = C.c_void_p
         L.tronref_host_alloc.argtypes = [C.c_size_t]
         L.tronref_host_free.argtypes = [C.c_void_p]
+        L.tronref_spoke_cs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.tronref_floatbits_to_halfbits.restype = C.c_ushort
         L.tronref_floatbits_to_halfbits.argtypes = [C.c_uint]
         L.tronref_halfbits_to_floatbits.restype = C.c_uint
@@ -237,6 +250,14 @@ class RefLib:
         a = _c(a).copy()
         self.lib.tronref_deapod(_ptr(a), n, nrep, m, sigma)
         return a
+
+    def spoke_cs(self, n, npe, skip, golden, degrid):
+        """(ct, st) of spokes 0..n-1 as the reference kernels compute them (SFU)."""
+        ct = np.zeros(n, dtype=np.float32); st = np.zeros(n, dtype=np.float32)
+        rc = self.lib.tronref_spoke_cs(_ptr(ct), _ptr(st), n, npe, skip, int(golden), int(degrid))
+        if rc:
+            raise RuntimeError("tronref_spoke_cs failed")
+        return ct, st
 
     def adj_stage_ms(self, samples, reps=3):
         ms = (C.c_float * 8)()

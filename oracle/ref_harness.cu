@@ -206,6 +206,32 @@ int tronref_adj_stage_ms(const float2 *h_samples, float ms[8], int reps)
     return 0;
 }
 
+/* sin/cos of every spoke exactly as the reference kernels obtain them
+ * (tron.cu:509-511 for gridding, 555-559 for degridding): same expressions,
+ * the reference's own modang() and PHI, same compile flags, same SFU. */
+__global__ void harness_spoke_cs(float *ct, float *st, int n, int npe, int skip, int golden, int degrid)
+{
+    for (int pe = blockIdx.x * blockDim.x + threadIdx.x; pe < n; pe += blockDim.x * gridDim.x) {
+        float t;
+        if (degrid) t = golden ? modang(PHI*(pe + skip)) : pe*M_PI/float(npe);
+        else t = golden ? modang(PHI * float(pe + skip)) : pe*2.0f*M_PI / float(npe) + M_PI*0.5f;
+        float s, c;
+        __sincosf(t, &s, &c);
+        ct[pe] = c; st[pe] = s;
+    }
+}
+
+int tronref_spoke_cs(float *h_ct, float *h_st, int n, int npe, int skip, int golden, int degrid)
+{
+    float *d = NULL;
+    if (cudaMalloc(&d, 2 * (size_t)n * sizeof(float)) != cudaSuccess) return -1;
+    harness_spoke_cs<<<64, 128>>>(d, d + n, n, npe, skip, golden, degrid);
+    cudaMemcpy(h_ct, d, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_st, d + n, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return 0;
+}
+
 /* host-side reference objects linked in from ra.cu / float16.cu */
 int tronref_ra_read(ra_t *a, const char *path) { return ra_read(a, path); }
 int tronref_ra_write(ra_t *a, const char *path) { return ra_write(a, path); }

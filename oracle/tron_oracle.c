@@ -169,9 +169,25 @@ static void grid_tap(void *vctx, int pe, int r, int ridx, float wgt)
     }
 }
 
+/* Optional trig override.  The reference takes sin/cos from the GPU's special
+ * function unit (__sincosf, tron.cu:511,559), which libm cannot reproduce bit
+ * for bit; for axis-aligned linear spokes that decides whole rows of edge taps.
+ * The golden fixtures therefore carry the SFU values of every spoke (dumped by
+ * oracle/_ref on the GPU), indexed by pe + skip for golden angles and by pe for
+ * linear ones, and the tests install them here. */
+static const float *g_trig_ct = NULL, *g_trig_st = NULL;
+static int g_trig_n = 0;
+
+void oracle_set_trig_table(const float *ct, const float *st, int n)
+{
+    g_trig_ct = ct; g_trig_st = st; g_trig_n = (ct && st) ? n : 0;
+}
+
 static void spoke_tables(float *ct, float *st, int npe, int skip_angles, int golden, int degrid)
 {
     for (int pe = 0; pe < npe; ++pe) {
+        int k = golden ? pe + skip_angles : pe;
+        if (k >= 0 && k < g_trig_n) { ct[pe] = g_trig_ct[k]; st[pe] = g_trig_st[k]; continue; }
         float t = degrid ? oracle_spoke_angle_degrid(pe, npe, skip_angles, golden)
                          : oracle_spoke_angle_grid(pe, npe, skip_angles, golden);
         st[pe] = sinf(t);

@@ -60,6 +60,9 @@ float oracle_modang(float x);
 float oracle_spoke_angle_grid(int pe, int npe, int skip_angles, int golden);
 float oracle_spoke_angle_degrid(int pe, int npe, int skip_angles, int golden);
 
+/* install (or clear with NULL) SFU sin/cos values of the spokes, see tron_oracle.c */
+void oracle_set_trig_table(const float *ct, const float *st, int n);
+
 /* array kernels */
 void oracle_precompensate(ocplx *nudata, int nchan, int nro, int npe1work);
 void oracle_gridradial2d(ocplx *udata, const ocplx *nudata, int nxos, int nchan,

@@ -1,0 +1,406 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+  (a) the unmodified reference compiled in place (oracle/_ref, same GPU), and
+  (b) the CPU oracle (oracle/tron_oracle.c).
+
+Tolerances are the north star's: relative L2 <= 1e-5 for fp32, <= 2e-3 with fp16
+storage, and bit-exact sample<->cell index maps (checked with indicator probes
+pushed through the reference kernels themselves).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import PARITY_CASES, case_input, rel_l2, synth_complex
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_F16 = 2e-3
+
+
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def flags_to_cfg(dims, flags, **extra):
+    import tron_b200 as t
+    kw = dict(flags)
+    kw.update(extra)
+    return t.make_config(dims, **kw)
+
+
+def run_ref(ref, dims, flags, h_in):
+    ref.configure(dims, flags.get("adjoint", False), golden=flags.get("golden", False),
+                  gridos=flags.get("gridos", 2.0), kernwidth=flags.get("kernwidth", 2.0),
+                  undersamp=flags.get("undersamp", 1.0), prof_slide=flags.get("prof_slide", 0),
+                  skip_angles=flags.get("skip_angles", 0))
+    return ref.recon(h_in)
+
+
+# ------------------------------------------------------------------ whole pipeline
+@pytest.mark.parametrize("name", sorted(PARITY_CASES))
+def test_pipeline_vs_reference(lib, reflib, name):
+    import tron_b200 as t
+    torch_cuda()
+    dims, flags = PARITY_CASES[name]
+    h_in = case_input(name)
+    want = run_ref(reflib, dims, flags, h_in)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        assert [int(x) for x in p.geom.out_dims] == reflib.out_dims
+        g = p.geom.as_dict()
+        for k, v in reflib.geom.items():
+            assert g[k] == v, k
+        got = p.recon_host(h_in)
+    assert got.shape == want.shape
+    assert rel_l2(got, want) <= TOL_F32, rel_l2(got, want)
+
+
+@pytest.mark.parametrize("name", sorted(PARITY_CASES))
+def test_pipeline_vs_oracle(lib, oracle, name):
+    import tron_b200 as t
+    torch_cuda()
+    dims, flags = PARITY_CASES[name]
+    h_in = case_input(name)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    oracle.set_trig_table(gold["ct"], gold["st"])       # SFU sin/cos of the spokes, see tron_oracle.c
+    cfg = oracle.config(dims, flags.get("adjoint", False), golden=flags.get("golden", False),
+                        gridos=flags.get("gridos", 2.0), kernwidth=flags.get("kernwidth", 2.0),
+                        undersamp=flags.get("undersamp", 1.0), prof_slide=flags.get("prof_slide", 0),
+                        skip_angles=flags.get("skip_angles", 0))
+    want = oracle.recon(cfg, h_in)
+    oracle.set_trig_table(None)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        got = p.recon_host(h_in)
+    assert rel_l2(got, want) <= TOL_F32, rel_l2(got, want)
+
+
+def test_pipeline_more_than_six_coils(lib, reflib_wide):
+    """nc > MAXCHAN needs the widened reference build (tron.h:51)."""
+    import tron_b200 as t
+    torch_cuda()
+    dims = [16, 1, 64, 80, 1]
+    flags = dict(adjoint=True, golden=True, undersamp=0.5, prof_slide=16)
+    h_in = synth_complex((int(np.prod(dims)),), stream=40)
+    want = run_ref(reflib_wide, dims, flags, h_in)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        got = p.recon_host(h_in)
+    assert rel_l2(got, want) <= TOL_F32
+
+
+def test_six_coil_chunks_combine_like_reference(lib, reflib):
+    """with the stock reference, nc > 6 is run in <= 6-coil chunks and RSS-combined."""
+    import tron_b200 as t
+    torch_cuda()
+    nc, nro, npe = 8, 64, 48
+    s = synth_complex((npe, nro, nc), stream=41)
+    flags = dict(adjoint=True, golden=True)
+    sos = np.zeros(32 * 32, dtype=np.float64)
+    for c0, c1 in ((0, 6), (6, 8)):
+        chunk = np.ascontiguousarray(s[:, :, c0:c1])
+        out = run_ref(reflib, [c1 - c0, 1, nro, npe, 1], flags, chunk.ravel())
+        sos += np.abs(out.astype(np.complex128)) ** 2
+    want = np.sqrt(sos)
+    with t.Plan(flags_to_cfg([nc, 1, nro, npe, 1], flags)) as p:
+        got = p.recon_host(s.ravel())
+    assert np.all(got.imag == 0)
+    assert rel_l2(got.real, want) <= TOL_F32
+
+
+# ------------------------------------------------------------------ stage level
+def _grid_mine(t, torch, samples, nchan, nro, npe, nslices=1, **flags):
+    """samples: (npe_total, nro, nchan) complex64 -> (nslices, n, n, nchan) via tron_grid_device."""
+    cfg = t.make_config([nchan, 1, nro, samples.shape[0], 1], adjoint=True, **flags)
+    with t.Plan(cfg) as p:
+        n = p.geom.nxos
+        ns = p.geom.slice_end - p.geom.slice_begin
+        d_s = torch.from_numpy(samples.view(np.float32).copy()).cuda()
+        d_g = torch.empty((ns, nchan, n, n, 2), dtype=torch.float32, device="cuda")
+        d_i = torch.empty((ns, n, n, nchan, 2), dtype=torch.float32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        p.grid_device(d_g.data_ptr(), d_s.data_ptr(), 0, ns, st)
+        p.grid_to_interleaved(d_i.data_ptr(), d_g.data_ptr(), ns, st)
+        torch.cuda.synchronize()
+        out = d_i.cpu().numpy().view(np.complex64)[..., 0]
+        return out, p.geom.as_dict()
+
+
+@pytest.mark.parametrize("golden,W,gridos,nchan", [(True, 2.0, 2.0, 2), (False, 2.0, 2.0, 6), (True, 3.0, 2.0, 1),
+                                                    (True, 2.0, 1.5, 4), (True, 2.5, 2.0, 2)])
+def test_grid_stage_vs_reference(lib, reflib, oracle, golden, W, gridos, nchan):
+    import tron_b200 as t
+    torch = torch_cuda()
+    nro, npe, skip = 128, 72, 5
+    s = synth_complex((npe, nro, nchan), stream=50 + nchan)
+    mine, geom = _grid_mine(t, torch, s, nchan, nro, npe, golden=golden, kernwidth=W, gridos=gridos, skip_angles=skip)
+    n = geom["nxos"]
+    pre = oracle.precompensate(s, nchan, nro, npe)          # tron.cu:405-416 on the host
+    want = reflib.grid(pre, n, nchan, nro, npe, W=W, gridos=gridos, skip=skip, golden=golden)
+    assert np.array_equal(mine[0] != 0, want != 0), "tap support differs"
+    assert rel_l2(mine[0], want) <= TOL_F32, rel_l2(mine[0], want)
+
+
+def _indicator_probe_grid(t, torch, reflib, nro, npe, nchan, golden, W, gridos, skip, sample_ids):
+    """Each channel carries ONE unit sample; the non-zero cells of that channel are exactly
+    the cells that sample contributes to.  Returns the support from both implementations."""
+    s = np.zeros((npe, nro, nchan), dtype=np.complex64)
+    for ch, sid in enumerate(sample_ids):
+        s[sid // nro, sid % nro, ch] = 1.0
+    mine, geom = _grid_mine(t, torch, s, nchan, nro, npe, golden=golden, kernwidth=W, gridos=gridos, skip_angles=skip)
+    want = reflib.grid(s, geom["nxos"], nchan, nro, npe, W=W, gridos=gridos, skip=skip, golden=golden)
+    return mine[0], want
+
+
+@pytest.mark.parametrize("golden,W,gridos", [(True, 2.0, 2.0), (False, 2.0, 2.0), (True, 2.0, 1.5), (True, 3.0, 2.0)])
+def test_grid_index_map_bit_exact(lib, reflib, golden, W, gridos):
+    """Sample -> cell index map, every sample of a small geometry, against the stock reference kernel."""
+    import tron_b200 as t
+    torch = torch_cuda()
+    nro, npe, skip, nchan = 32, 12, 7, 6
+    a = (2.0 - 2.0 / npe) / nro
+    b = 1.0 / npe
+    total = nro * npe
+    ntaps = 0
+    for base in range(0, total, nchan):
+        ids = [min(base + c, total - 1) for c in range(nchan)]
+        mine, want = _indicator_probe_grid(t, torch, reflib, nro, npe, nchan, golden, W, gridos, skip, ids)
+        assert np.array_equal(mine != 0, want != 0), "index map differs for samples %s" % ids
+        for ch, sid in enumerate(ids):
+            sdc = a * abs((sid % nro) - nro // 2) + b       # folded density compensation
+            m, w = mine[..., ch].real, want[..., ch].real * sdc
+            nz = w != 0
+            ntaps += int(nz.sum())
+            if nz.any():
+                assert np.max(np.abs(m[nz] - w[nz]) / np.abs(w[nz])) < 2e-5
+    assert ntaps > 0
+
+
+def test_grid_index_map_bit_exact_wide(lib, reflib_wide):
+    """Same probe on a larger geometry, 64 samples per launch through the widened build."""
+    import tron_b200 as t
+    torch = torch_cuda()
+    nro, npe, skip, nchan = 64, 40, 11, 64
+    total = nro * npe
+    rng = np.random.default_rng(7)
+    order = rng.permutation(total)
+    for base in range(0, total, nchan):
+        ids = [int(order[min(base + c, total - 1)]) for c in range(nchan)]
+        mine, want = _indicator_probe_grid(t, torch, reflib_wide, nro, npe, nchan, True, 2.0, 2.0, skip, ids)
+        assert np.array_equal(mine != 0, want != 0), "index map differs for samples %s" % ids
+
+
+def _degrid_mine(t, torch, grid, n_img, nchan, **flags):
+    """grid: (n, n, nchan) complex64 in the reference's interleaved order -> (npe, nro, nchan)."""
+    cfg = t.make_config([nchan, 1, n_img, n_img, 1], adjoint=False, **flags)
+    with t.Plan(cfg) as p:
+        g = p.geom
+        assert g.nxos == grid.shape[0]
+        d_g = torch.from_numpy(grid.view(np.float32).copy()).cuda()
+        d_s = torch.empty((g.npe1work, g.nro, nchan, 2), dtype=torch.float32, device="cuda")
+        p.degrid_device(d_s.data_ptr(), d_g.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return d_s.cpu().numpy().view(np.complex64)[..., 0], g.as_dict()
+
+
+@pytest.mark.parametrize("golden,W,nchan", [(False, 2.0, 1), (True, 2.0, 2), (True, 3.0, 4), (False, 2.5, 2), (True, 6.0, 2)])
+def test_degrid_stage_vs_reference(lib, reflib, golden, W, nchan):
+    import tron_b200 as t
+    torch = torch_cuda()
+    n_img, skip = 48, 3
+    n = 2 * n_img
+    u = synth_complex((n, n, nchan), stream=60 + nchan)
+    mine, geom = _degrid_mine(t, torch, u, n_img, nchan, golden=golden, kernwidth=W, skip_angles=skip)
+    want = reflib.degrid(u, n, nchan, geom["nro"], geom["npe1work"], W=W, gridos=2.0, skip=skip, golden=golden)
+    assert rel_l2(mine, want) <= TOL_F32, rel_l2(mine, want)
+
+
+@pytest.mark.parametrize("golden", [True, False])
+def test_degrid_index_map_bit_exact(lib, reflib, golden):
+    """Cell -> sample index map with indicator grids (one unit cell per channel)."""
+    import tron_b200 as t
+    torch = torch_cuda()
+    n_img, nchan, skip = 12, 6, 2
+    n = 2 * n_img
+    for base in range(0, n * n, nchan):
+        u = np.zeros((n, n, nchan), dtype=np.complex64)
+        for ch in range(nchan):
+            cid = min(base + ch, n * n - 1)
+            u[cid // n, cid % n, ch] = 1.0
+        mine, geom = _degrid_mine(t, torch, u, n_img, nchan, golden=golden, skip_angles=skip)
+        want = reflib.degrid(u, n, nchan, geom["nro"], geom["npe1work"], W=2.0, gridos=2.0, skip=skip, golden=golden)
+        assert np.array_equal(mine != 0, want != 0), "index map differs at cell %d" % base
+        nz = want != 0
+        if nz.any():
+            assert np.max(np.abs(mine[nz] - want[nz]) / np.abs(want[nz])) < 2e-5
+
+
+# ------------------------------------------------------------------ sharding, batching, legacy, CLI
+def test_slice_shards_concatenate(lib):
+    import tron_b200 as t
+    torch_cuda()
+    dims = [2, 1, 64, 200, 1]
+    flags = dict(adjoint=True, golden=True, undersamp=0.25, prof_slide=5, skip_angles=2)
+    h_in = synth_complex((int(np.prod(dims)),), stream=70)
+    with t.Plan(flags_to_cfg(dims, flags, batch_slices=7)) as p:
+        full = p.recon_host(h_in)
+        nz = p.geom.nz
+    parts = []
+    for rank in range(3):
+        lo, hi = t.shard_slices(nz, rank, 3)
+        with t.Plan(flags_to_cfg(dims, flags, slices=(lo, hi), batch_slices=4)) as p:
+            g = p.geom
+            part = p.recon_host(h_in[int(g.shard_in_offset):int(g.shard_in_offset + g.shard_in_elems)])
+            assert part.size == int(g.shard_out_elems)
+            parts.append(part)
+    assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_coil_shards_sum_of_squares(lib):
+    import tron_b200 as t
+    torch_cuda()
+    dims = [8, 1, 64, 48, 1]
+    flags = dict(adjoint=True, golden=True)
+    h_in = synth_complex((int(np.prod(dims)),), stream=71)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        full = p.recon_host(h_in)
+    sos = np.zeros(full.size, dtype=np.float32)
+    for c0, c1 in ((0, 2), (2, 6), (6, 8)):
+        with t.Plan(flags_to_cfg(dims, flags, coils=(c0, c1), sos_partial=True)) as p:
+            sos += p.recon_host(h_in)
+    assert rel_l2(np.sqrt(sos), full.real) <= 1e-6
+
+
+def test_device_api_matches_host_api(lib):
+    import tron_b200 as t
+    torch = torch_cuda()
+    dims, flags = PARITY_CASES["P2_slide"]
+    h_in = case_input("P2_slide")
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        want = p.recon_host(h_in)
+        d_in = torch.from_numpy(h_in.view(np.float32).copy()).cuda()
+        d_out = torch.zeros(want.size * 2, dtype=torch.float32, device="cuda")
+        p.recon_device(d_out.data_ptr(), d_in.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert p.last_launches() > 0
+        got = d_out.cpu().numpy().view(np.complex64)
+    assert np.array_equal(got, want)
+
+
+def test_legacy_recon_radial2d(lib):
+    import tron_b200 as t
+    torch_cuda()
+    dims, flags = PARITY_CASES["P3_6ch"]
+    h_in = case_input("P3_6ch")
+    cfg = flags_to_cfg(dims, flags)
+    with t.Plan(cfg) as p:
+        want = p.recon_host(h_in)
+    assert lib.tron_set_config(C.byref(cfg)) == 0
+    got = np.zeros_like(want)
+    lib.recon_radial2d(got.ctypes.data_as(C.c_void_p), h_in.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(got, want)
+
+
+def test_legacy_kernels_match_reference(lib, reflib):
+    """gridradial2d / degridradial2d compatibility kernels, odd launch shape."""
+    torch = torch_cuda()
+    nro, npe, nchan, n = 64, 30, 2, 64
+    s = synth_complex((npe, nro, nchan), stream=72)
+    want = reflib.grid(s, n, nchan, nro, npe, W=2.0, gridos=2.0, skip=3, golden=True)
+    d_s = torch.from_numpy(s.view(np.float32).copy()).cuda()
+    d_u = torch.zeros((n, n, nchan, 2), dtype=torch.float32, device="cuda")
+    assert lib.tron_launch_gridradial2d(C.c_void_p(d_u.data_ptr()), C.c_void_p(d_s.data_ptr()), n, nchan, nro, npe,
+                                        2.0, 2.0, 3, 1, 37, 96, None) == 0
+    torch.cuda.synchronize()
+    got = d_u.cpu().numpy().view(np.complex64)[..., 0]
+    assert np.array_equal(got != 0, want != 0)
+    assert rel_l2(got, want) <= TOL_F32
+    u = synth_complex((n, n, nchan), stream=73)
+    want = reflib.degrid(u, n, nchan, nro, npe, W=2.0, gridos=2.0, skip=3, golden=True)
+    d_u = torch.from_numpy(u.view(np.float32).copy()).cuda()
+    d_o = torch.zeros((npe, nro, nchan, 2), dtype=torch.float32, device="cuda")
+    assert lib.tron_launch_degridradial2d(C.c_void_p(d_o.data_ptr()), C.c_void_p(d_u.data_ptr()), n, nchan, nro, npe,
+                                          2.0, 2.0, 3, 1, 37, 96, None) == 0
+    torch.cuda.synchronize()
+    got = d_o.cpu().numpy().view(np.complex64)[..., 0]
+    assert rel_l2(got, want) <= TOL_F32
+
+
+def test_cli_matches_reference_binary(lib, tmp_path):
+    import tron_b200 as t
+    torch_cuda()
+    ref_exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "tron_ref")
+    if not os.path.isfile(ref_exe):
+        pytest.skip("oracle/_ref/tron_ref not built")
+    for name, args in (("P2_slide", ["-a", "-G", "-u", "0.25", "-d", "7", "-s", "3"]), ("P4_fwd", [])):
+        dims, _ = PARITY_CASES[name]
+        fin = str(tmp_path / (name + "_in.ra"))
+        t.ra_write(fin, case_input(name), dims=dims)
+        f_ref, f_new = str(tmp_path / "ref.ra"), str(tmp_path / "new.ra")
+        subprocess.run([ref_exe] + args + [fin, f_ref], check=True, timeout=300)
+        subprocess.run([t.CLI_PATH] + args + [fin, f_new], check=True, timeout=300)
+        a, da, ta, ba = t.ra_read(f_ref)
+        b, db, tb, bb = t.ra_read(f_new)
+        assert (da, ta, ba) == (db, tb, bb)
+        assert open(f_ref, "rb").read(88) == open(f_new, "rb").read(88)      # identical 5-D header bytes
+        assert rel_l2(b, a) <= TOL_F32
+    assert subprocess.run([t.CLI_PATH], capture_output=True).returncode == 1
+    assert subprocess.run([t.CLI_PATH, "-h"], capture_output=True).returncode == 1
+    assert subprocess.run([t.CLI_PATH, "-Z", "x.ra"], capture_output=True).returncode == 1
+
+
+# ------------------------------------------------------------------ fp16 storage
+def test_fp16_storage_adjoint(lib):
+    import tron_b200 as t
+    torch_cuda()
+    dims, flags = PARITY_CASES["P3_6ch"]
+    h_in = case_input("P3_6ch")
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        want = p.recon_host(h_in)
+    h16 = h_in.view(np.float32).astype(np.float16)
+    with t.Plan(flags_to_cfg(dims, flags, half_in=True, half_out=True)) as p:
+        got16 = p.recon_host(h16)
+    got = got16.astype(np.float32).reshape(-1, 2)
+    got = got[:, 0] + 1j * got[:, 1]
+    assert rel_l2(got, want) <= TOL_F16, rel_l2(got, want)
+
+
+def test_fp16_storage_forward(lib):
+    import tron_b200 as t
+    torch_cuda()
+    dims, flags = PARITY_CASES["P5_fwd4"]
+    h_in = case_input("P5_fwd4")
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        want = p.recon_host(h_in)
+    h16 = h_in.view(np.float32).astype(np.float16)
+    with t.Plan(flags_to_cfg(dims, flags, half_in=True, half_out=True)) as p:
+        got16 = p.recon_host(h16)
+    got = got16.astype(np.float32).reshape(-1, 2)
+    got = got[:, 0] + 1j * got[:, 1]
+    assert rel_l2(got, want) <= TOL_F16, rel_l2(got, want)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_linearity_and_shard_consistency(lib):
+    """BASELINE config 2 geometry (nc=6, nro=512, 204-spoke window, slide 21), a 40-slice stretch:
+    per-coil linearity A(x+2y) = A(x) + 2A(y) and batch-size independence."""
+    import tron_b200 as t
+    torch_cuda()
+    npe1 = 204 + 21 * 39
+    dims = [6, 1, 512, npe1, 1]
+    flags = dict(adjoint=True, golden=True, undersamp=0.4, prof_slide=21)
+    x = synth_complex((int(np.prod(dims)),), stream=80)
+    y = synth_complex((int(np.prod(dims)),), stream=81)
+    with t.Plan(flags_to_cfg(dims, flags, per_coil_out=True, batch_slices=5)) as p:
+        assert p.geom.nz == 40 and p.geom.npe1work == 204
+        ax, ay = p.recon_host(x), p.recon_host(y)
+        axy = p.recon_host((x + 2 * y).astype(np.complex64))
+    assert rel_l2(axy, ax + 2 * ay) <= 2e-6
+    with t.Plan(flags_to_cfg(dims, flags, batch_slices=16)) as p:
+        rss = p.recon_host(x)
+    want = np.sqrt((np.abs(ax.reshape(-1, 6).astype(np.complex128)) ** 2).sum(axis=1))
+    assert rel_l2(rss.real, want) <= 1e-6

@@ -1,0 +1,458 @@
+/*
+ * fft.cu -- batched 2-D FFT with the surrounding passes fused in.
+ *
+ * Replaces, for the adjoint (tron.cu:631-635 and 764):
+ *     fftshift(INV) -> cufftExecC2C(INVERSE) -> fftshift(FWD) -> crop -> deapodkernel
+ *     -> coilcombinesos
+ * and for the forward direction (tron.cu:642-646):
+ *     pad -> deapodkernel(n = nxos, sigma = 1) -> fftshift(FWD) -> cufftExecC2C(FORWARD)
+ *     -> fftshift(INV)
+ * (/root/reference/src/tron.cu:161-178, 205-220, 255-268, 390-457).
+ *
+ * Both directions are two passes of 1-D transforms over lines that are
+ * contiguous in memory; each pass writes its result transposed so that the
+ * next pass (or the consumer) again reads contiguous lines:
+ *
+ *   adjoint  A: grid[ch][y][:]  --FFT_x-->  keep the nx centre frequencies  --> tmp[ch][b][y]
+ *            B: tmp[ch][b][:]   --FFT_y-->  keep nx, deapodise, |.|^2 over coils --> image[a][b]
+ *   forward  A: image[a][:][ch] (pad + deapodise on load) --FFT-->  tmp[ch][c][a]
+ *            B: tmp[ch][c][:]   (pad on load)             --FFT-->  grid[ch][r][c]
+ *
+ * The two fftshifts never move data: a circular shift by n/2 of the INPUT is a
+ * (-1)^k modulation of the output, a shift of the OUTPUT is an index offset in
+ * the store.  Crop = only the nx kept outputs are stored (the intermediate is
+ * nx/nxos the size of the grid); pad = zeros are written to shared memory, not
+ * read from HBM.  cuFFT conventions are kept: unnormalised, FORWARD e^{-i},
+ * INVERSE e^{+i}.
+ *
+ * The line transform is a Stockham autosort FFT in shared memory, radices
+ * 8/4/2 plus 3 and 5 (nxos = 384 occurs with -o 1.5), twiddles from a
+ * plan-time table computed in double precision.
+ */
+#include "tron_internal.h"
+#include <math.h>
+#include <vector>
+
+namespace tronb {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+/* multiply by s*i, s = +-1 */
+__device__ __forceinline__ float2 cmuli(float2 a, float s) { return make_float2(-s * a.y, s * a.x); }
+
+/* shared-memory index padding: one extra element every 8 keeps the strided
+ * Stockham accesses (stride = radix) off a single bank */
+__device__ __forceinline__ int phys(int i) { return i + (i >> 3); }
+static inline int phys_host(int i) { return i + (i >> 3); }
+
+template <int R> struct Dft;
+template <> struct Dft<2> {
+    __device__ static void run(float2 *v, float) {
+        float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    }
+};
+template <> struct Dft<4> {
+    __device__ static void run(float2 *v, float s) {
+        float2 p = cadd(v[0], v[2]), q = csub(v[0], v[2]);
+        float2 r = cadd(v[1], v[3]), t = cmuli(csub(v[1], v[3]), s);
+        v[0] = cadd(p, r); v[2] = csub(p, r);
+        v[1] = cadd(q, t); v[3] = csub(q, t);
+    }
+};
+template <> struct Dft<8> {
+    __device__ static void run(float2 *v, float s) {
+        float2 e[4] = { v[0], v[2], v[4], v[6] }, o[4] = { v[1], v[3], v[5], v[7] };
+        Dft<4>::run(e, s); Dft<4>::run(o, s);
+        const float h = 0.70710678118654752440f;
+        float2 w1 = make_float2(h, s * h), w3 = make_float2(-h, s * h);
+        o[1] = cmul(o[1], w1); o[2] = cmuli(o[2], s); o[3] = cmul(o[3], w3);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = cadd(e[k], o[k]); v[k + 4] = csub(e[k], o[k]); }
+    }
+};
+template <> struct Dft<3> {
+    __device__ static void run(float2 *v, float s) {
+        const float c = -0.5f, sn = 0.86602540378443864676f;
+        float2 t = cadd(v[1], v[2]), d = cmuli(csub(v[1], v[2]), s * sn);
+        float2 m = make_float2(fmaf(c, t.x, v[0].x), fmaf(c, t.y, v[0].y));
+        v[0] = cadd(v[0], t); v[1] = cadd(m, d); v[2] = csub(m, d);
+    }
+};
+template <> struct Dft<5> {
+    __device__ static void run(float2 *v, float s) {
+        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+        float2 a = cadd(v[1], v[4]), b = cadd(v[2], v[3]);
+        float2 c = csub(v[1], v[4]), d = csub(v[2], v[3]);
+        float2 m1 = make_float2(v[0].x + c1 * a.x + c2 * b.x, v[0].y + c1 * a.y + c2 * b.y);
+        float2 m2 = make_float2(v[0].x + c2 * a.x + c1 * b.x, v[0].y + c2 * a.y + c1 * b.y);
+        float2 n1 = cmuli(make_float2(s1 * c.x + s2 * d.x, s1 * c.y + s2 * d.y), s);
+        float2 n2 = cmuli(make_float2(s2 * c.x - s1 * d.x, s2 * c.y - s1 * d.y), s);
+        v[0] = cadd(v[0], cadd(a, b));
+        v[1] = cadd(m1, n1); v[4] = csub(m1, n1);
+        v[2] = cadd(m2, n2); v[3] = csub(m2, n2);
+    }
+};
+
+/* one Stockham stage of radix R over L lines held in shared memory */
+template <int R>
+__device__ __forceinline__ void stockham_stage(const float2 *src, float2 *dst, const float2 *tw,
+                                               int n, int Ns, int L, int pitch, float sgn)
+{
+    const int nb = n / R;
+    const int tstep = n / (Ns * R);
+    for (int idx = threadIdx.x; idx < nb * L; idx += blockDim.x) {
+        const int l = idx / nb, j = idx - l * nb;
+        const int k = j % Ns;
+        const float2 *s = src + l * pitch;
+        float2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = s[phys(j + t * nb)];
+        if (Ns > 1) {
+#pragma unroll
+            for (int t = 1; t < R; ++t) {
+                float2 w = tw[t * k * tstep];
+                w.y *= sgn;
+                v[t] = cmul(v[t], w);
+            }
+        }
+        Dft<R>::run(v, sgn);
+        float2 *d = dst + l * pitch;
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; ++t) d[phys(j0 + t * Ns)] = v[t];
+    }
+}
+
+struct Factors { int nfac; int fac[16]; };
+
+/* transforms L lines in place of bufA/bufB ping-pong; returns the buffer holding the result */
+__device__ float2 *fft_lines(float2 *bufA, float2 *bufB, const float2 *tw, int n, int L, int pitch,
+                             const Factors &f, float sgn)
+{
+    int Ns = 1;
+    float2 *src = bufA, *dst = bufB;
+    for (int s = 0; s < f.nfac; ++s) {
+        const int R = f.fac[s];
+        switch (R) {
+        case 8: stockham_stage<8>(src, dst, tw, n, Ns, L, pitch, sgn); break;
+        case 4: stockham_stage<4>(src, dst, tw, n, Ns, L, pitch, sgn); break;
+        case 2: stockham_stage<2>(src, dst, tw, n, Ns, L, pitch, sgn); break;
+        case 3: stockham_stage<3>(src, dst, tw, n, Ns, L, pitch, sgn); break;
+        default: stockham_stage<5>(src, dst, tw, n, Ns, L, pitch, sgn); break;
+        }
+        Ns *= R;
+        __syncthreads();
+        float2 *t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
+struct PassGeom {
+    int n, nkeep, L, pitch;
+    Factors f;
+};
+
+__device__ __forceinline__ void load_twiddles(float2 *stw, const float2 *tw, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) stw[i] = tw[i];
+}
+
+/* ---------------- adjoint pass A: FFT along x, crop, transpose ---------------- */
+__global__ void __launch_bounds__(256)
+adj_pass_a_kernel(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw,
+                  const PassGeom p)
+{
+    extern __shared__ float2 smem[];
+    const int n = p.n, L = p.L, pitch = p.pitch, nkeep = p.nkeep;
+    float2 *bufA = smem, *bufB = smem + L * pitch, *stw = smem + 2 * L * pitch;
+    const int y0 = blockIdx.x * L;
+    const size_t plane = blockIdx.y;
+    load_twiddles(stw, tw, n);
+    const float2 *g = grid + plane * (size_t)n * n + (size_t)y0 * n;
+    for (int idx = threadIdx.x; idx < L * n; idx += blockDim.x) {
+        int l = idx / n, j = idx - l * n;
+        bufA[l * pitch + phys(j)] = (y0 + l < n) ? g[idx] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    float2 *res = fft_lines(bufA, bufB, stw, n, L, pitch, p.f, +1.f);
+    const int w = (n - nkeep) / 2, h = n / 2;
+    float2 *out = tmp + plane * (size_t)nkeep * n + y0;
+    for (int idx = threadIdx.x; idx < nkeep * L; idx += blockDim.x) {
+        int b = idx / L, l = idx - b * L;
+        int k = b + w - h; if (k < 0) k += n;
+        float2 v = res[l * pitch + phys(k)];
+        if (k & 1) { v.x = -v.x; v.y = -v.y; }
+        if (y0 + l < n) out[(size_t)b * n + l] = v;
+    }
+}
+
+/* ------- adjoint pass B: FFT along y, crop, deapodise, coil combine ------- */
+#define PASSB_MAXO 16
+__global__ void __launch_bounds__(256)
+adj_pass_b_kernel(const float2 *__restrict__ tmp, void *__restrict__ outv, const float *__restrict__ deapod,
+                  const float2 *__restrict__ tw, const PassGeom p, int nch, int nc_total, int ch0, int mode,
+                  int half_out)
+{
+    extern __shared__ float2 smem[];
+    const int n = p.n, L = p.L, pitch = p.pitch, nkeep = p.nkeep;
+    float2 *bufA = smem, *bufB = smem + L * pitch, *stw = smem + 2 * L * pitch;
+    const int b0 = blockIdx.x * L;
+    const int slice = blockIdx.y;
+    const int w = (n - nkeep) / 2, h = n / 2;
+    load_twiddles(stw, tw, n);
+    float acc[PASSB_MAXO];
+#pragma unroll
+    for (int o = 0; o < PASSB_MAXO; ++o) acc[o] = 0.f;
+    const size_t img = (size_t)nkeep * nkeep;
+
+    for (int ch = 0; ch < nch; ++ch) {
+        const float2 *src = tmp + ((size_t)slice * nch + ch) * (size_t)nkeep * n + (size_t)b0 * n;
+        for (int idx = threadIdx.x; idx < L * n; idx += blockDim.x) {
+            int l = idx / n, j = idx - l * n;
+            bufA[l * pitch + phys(j)] = (b0 + l < nkeep) ? src[idx] : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        float2 *res = fft_lines(bufA, bufB, stw, n, L, pitch, p.f, +1.f);
+#pragma unroll
+        for (int o = 0; o < PASSB_MAXO; ++o) {
+            int idx = threadIdx.x + o * blockDim.x;
+            if (idx < nkeep * L) {
+                int a = idx / L, l = idx - a * L;
+                if (b0 + l < nkeep) {
+                    int k = a + w - h; if (k < 0) k += n;
+                    float2 v = res[l * pitch + phys(k)];
+                    float s = __ldg(deapod + (size_t)a * nkeep + b0 + l);
+                    if (k & 1) s = -s;
+                    v.x *= s; v.y *= s;
+                    size_t pix = (size_t)a * nkeep + b0 + l;
+                    if (mode == 0 || mode == 3) acc[o] += v.x * v.x + v.y * v.y;
+                    else if (mode == 1) {
+                        if (half_out) ((__half2 *)outv)[(size_t)slice * img + pix] = __float22half2_rn(v);
+                        else ((float2 *)outv)[(size_t)slice * img + pix] = v;
+                    } else {
+                        size_t o2 = ((size_t)slice * img + pix) * nc_total + ch0 + ch;
+                        if (half_out) ((__half2 *)outv)[o2] = __float22half2_rn(v);
+                        else ((float2 *)outv)[o2] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (mode == 0 || mode == 3) {
+#pragma unroll
+        for (int o = 0; o < PASSB_MAXO; ++o) {
+            int idx = threadIdx.x + o * blockDim.x;
+            if (idx < nkeep * L) {
+                int a = idx / L, l = idx - a * L;
+                if (b0 + l < nkeep) {
+                    size_t pix = (size_t)slice * img + (size_t)a * nkeep + b0 + l;
+                    if (mode == 3) ((float *)outv)[pix] = acc[o];
+                    else {
+                        float2 v = make_float2(sqrtf(acc[o]), 0.f);      /* tron.cu:263-264 */
+                        if (half_out) ((__half2 *)outv)[pix] = __float22half2_rn(v);
+                        else ((float2 *)outv)[pix] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* ------- forward pass A: pad + deapodise on load, FFT along columns ------- */
+__global__ void __launch_bounds__(256)
+fwd_pass_a_kernel(const void *__restrict__ imgv, float2 *__restrict__ tmp, const float *__restrict__ deapod,
+                  const float2 *__restrict__ tw, const PassGeom p, int nc_total, int ch0, int half_in)
+{
+    extern __shared__ float2 smem[];
+    const int n = p.n, L = p.L, pitch = p.pitch, nx = p.nkeep;
+    float2 *bufA = smem, *bufB = smem + L * pitch, *stw = smem + 2 * L * pitch;
+    const int a0 = blockIdx.x * L;
+    const int ch = blockIdx.y;
+    const int w = (n - nx) / 2, h = n / 2;
+    load_twiddles(stw, tw, n);
+    for (int idx = threadIdx.x; idx < L * pitch; idx += blockDim.x) bufA[idx] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < L * nx; idx += blockDim.x) {
+        int l = idx / nx, b = idx - l * nx, a = a0 + l;
+        /* pad drops source row 0 and column 0 (tron.cu:449-450) */
+        if (a >= 1 && a < nx && b >= 1) {
+            size_t e = ((size_t)a * nx + b) * nc_total + ch0 + ch;
+            float2 v = half_in ? __half22float2(((const __half2 *)imgv)[e]) : ((const float2 *)imgv)[e];
+            float s = __ldg(deapod + (size_t)a * nx + b);
+            bufA[l * pitch + phys(b + w)] = make_float2(v.x * s, v.y * s);
+        }
+    }
+    __syncthreads();
+    float2 *res = fft_lines(bufA, bufB, stw, n, L, pitch, p.f, -1.f);
+    float2 *out = tmp + (size_t)ch * n * nx + a0;
+    for (int idx = threadIdx.x; idx < n * L; idx += blockDim.x) {
+        int c = idx / L, l = idx - c * L;
+        int k = c + h; if (k >= n) k -= n;
+        float2 v = res[l * pitch + phys(k)];
+        if (k & 1) { v.x = -v.x; v.y = -v.y; }
+        if (a0 + l < nx) out[(size_t)c * nx + l] = v;
+    }
+}
+
+/* ------- forward pass B: pad on load, FFT along rows, planar grid out ------- */
+__global__ void __launch_bounds__(256)
+fwd_pass_b_kernel(const float2 *__restrict__ tmp, float2 *__restrict__ grid, const float2 *__restrict__ tw,
+                  const PassGeom p)
+{
+    extern __shared__ float2 smem[];
+    const int n = p.n, L = p.L, pitch = p.pitch, nx = p.nkeep;
+    float2 *bufA = smem, *bufB = smem + L * pitch, *stw = smem + 2 * L * pitch;
+    const int c0 = blockIdx.x * L;
+    const int ch = blockIdx.y;
+    const int w = (n - nx) / 2, h = n / 2;
+    load_twiddles(stw, tw, n);
+    for (int idx = threadIdx.x; idx < L * pitch; idx += blockDim.x) bufA[idx] = make_float2(0.f, 0.f);
+    __syncthreads();
+    const float2 *src = tmp + ((size_t)ch * n + c0) * nx;
+    for (int idx = threadIdx.x; idx < L * nx; idx += blockDim.x) {
+        int l = idx / nx, a = idx - l * nx;
+        if (c0 + l < n) bufA[l * pitch + phys(a + w)] = src[idx];
+    }
+    __syncthreads();
+    float2 *res = fft_lines(bufA, bufB, stw, n, L, pitch, p.f, -1.f);
+    float2 *out = grid + (size_t)ch * n * n + c0;
+    for (int idx = threadIdx.x; idx < n * L; idx += blockDim.x) {
+        int r = idx / L, l = idx - r * L;
+        int k = r + h; if (k >= n) k -= n;
+        float2 v = res[l * pitch + phys(k)];
+        if (k & 1) { v.x = -v.x; v.y = -v.y; }
+        if (c0 + l < n) out[(size_t)r * n + l] = v;
+    }
+}
+
+/* ------- deapodisation tables (reciprocal weights), tron.cu:351-370, 390-402 ------- */
+__device__ __forceinline__ float kb_hat(float u, float kernwidth)
+{
+    float J = 2.0f * kernwidth;
+    float beta = 2.34f * 2.0f * kernwidth;
+    float r = (float)(3.14159265358979323846 * (double)J * (double)u);
+    float q = r * r - beta * beta;
+    float y;
+    if (q > 0.f) { float z = sqrtf(q); y = __sinf(z) / z; }
+    else if (q < 0.f) { float z = sqrtf(-q); y = sinhf(z) / z; }
+    else y = 1.f;
+    return y;
+}
+
+/* table[a][b] = 1 / w(id), id = (a + off)*n + (b + off), evaluated exactly as
+ * deapodkernel does for an n x n array with the given sigma */
+__global__ void deapod_table_kernel(float *tab, int nt, int n, int off, float m, float sigma)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nt * nt; i += gridDim.x * blockDim.x) {
+        int a = i / nt, b = i - a * nt;
+        size_t id = (size_t)(a + off) * n + (b + off);
+        float x = (float)id / (float)n - (float)((n + 1) / 2);      /* tron.cu:395 (float division) */
+        float y = (float)(id % n) - (float)((n + 1) / 2);
+        float scale = 1.f / (float)n / sigma;
+        float wgt = kb_hat(x * scale, m) * kb_hat(y * scale, m);
+        tab[i] = 1.0f / (wgt > 0.f ? wgt : 1.f);
+    }
+}
+
+int launch_deapod_tables(float *adj_tab, float *fwd_tab, int nx, int nxos, float W, float gridos, cudaStream_t s)
+{
+    int blocks = (nx * nx + 255) / 256; if (blocks > 4096) blocks = 4096;
+    if (adj_tab) deapod_table_kernel<<<blocks, 256, 0, s>>>(adj_tab, nx, nx, 0, W, gridos);
+    if (fwd_tab) deapod_table_kernel<<<blocks, 256, 0, s>>>(fwd_tab, nx, nxos, (nxos - nx) / 2, W, 1.f);
+    TRON_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* ---------------- host side ---------------- */
+static bool factorize(int n, Factors &f)
+{
+    f.nfac = 0;
+    int m = n;
+    while (m % 8 == 0) { f.fac[f.nfac++] = 8; m /= 8; }
+    while (m % 4 == 0) { f.fac[f.nfac++] = 4; m /= 4; }
+    while (m % 2 == 0) { f.fac[f.nfac++] = 2; m /= 2; }
+    while (m % 3 == 0) { f.fac[f.nfac++] = 3; m /= 3; }
+    while (m % 5 == 0) { f.fac[f.nfac++] = 5; m /= 5; }
+    return m == 1 && f.nfac <= 16;
+}
+
+static PassGeom make_geom(const FftPlan &f)
+{
+    PassGeom p; p.n = f.n; p.nkeep = f.nkeep; p.L = f.lines;
+    p.pitch = phys_host(f.n) + 1;
+    p.f.nfac = f.nfac;
+    for (int i = 0; i < f.nfac; ++i) p.f.fac[i] = f.fac[i];
+    return p;
+}
+
+int fft_plan_init(FftPlan &f, int n, int nkeep)
+{
+    Factors fa;
+    if (n < 2 || n > 8192 || !factorize(n, fa)) {
+        set_error("oversampled grid size %d is not of the form 2^a 3^b 5^c <= 8192", n);
+        return TRON_EUNSUPPORTED;
+    }
+    if (nkeep > n || nkeep > 4096 || nkeep < 1) { set_error("bad image size %d for grid %d", nkeep, n); return TRON_EINVAL; }
+    f.n = n; f.nkeep = nkeep; f.nfac = fa.nfac;
+    for (int i = 0; i < fa.nfac; ++i) f.fac[i] = fa.fac[i];
+    int pitch = phys_host(n) + 1;
+    /* lines per CTA: bounded by shared memory (two buffers + twiddles) and by the
+     * PASSB_MAXO outputs a thread owns in pass B */
+    int L = 16;
+    while (L > 1 && ((size_t)(2 * L * pitch + n) * sizeof(float2) > 96 * 1024 || nkeep * L > PASSB_MAXO * 256)) L >>= 1;
+    f.lines = L;
+    f.smem = (size_t)(2 * L * pitch + n) * sizeof(float2);
+    if (f.smem > 227 * 1024) { set_error("grid size %d needs %zu B of shared memory", n, f.smem); return TRON_EUNSUPPORTED; }
+    std::vector<float2> tw(n);
+    for (int k = 0; k < n; ++k) {
+        double a = 2.0 * 3.14159265358979323846 * (double)k / (double)n;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    TRON_CUDA(cudaMalloc(&f.tw, n * sizeof(float2)));
+    TRON_CUDA(cudaMemcpy(f.tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    TRON_CUDA(cudaFuncSetAttribute(adj_pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem));
+    TRON_CUDA(cudaFuncSetAttribute(adj_pass_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem));
+    TRON_CUDA(cudaFuncSetAttribute(fwd_pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem));
+    TRON_CUDA(cudaFuncSetAttribute(fwd_pass_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem));
+    return 0;
+}
+
+void fft_plan_free(FftPlan &f)
+{
+    if (f.tw) cudaFree(f.tw);
+    f.tw = nullptr;
+}
+
+int launch_adj_fft(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
+{
+    PassGeom p = make_geom(f);
+    dim3 ga((f.n + p.L - 1) / p.L, a.nslices * a.nch);
+    adj_pass_a_kernel<<<ga, 256, f.smem, s>>>(a.grid, a.tmp, f.tw, p);
+    TRON_CUDA(cudaGetLastError());
+    dim3 gb((f.nkeep + p.L - 1) / p.L, a.nslices);
+    adj_pass_b_kernel<<<gb, 256, f.smem, s>>>(a.tmp, a.out, a.deapod, f.tw, p, a.nch, a.nc_total, a.ch0,
+                                              a.mode, a.half_out);
+    TRON_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)
+{
+    PassGeom p = make_geom(f);
+    dim3 ga((f.nkeep + p.L - 1) / p.L, a.nch);
+    fwd_pass_a_kernel<<<ga, 256, f.smem, s>>>(a.img, a.tmp, a.deapod, f.tw, p, a.nc_total, a.ch0, a.half_in);
+    TRON_CUDA(cudaGetLastError());
+    dim3 gb((f.n + p.L - 1) / p.L, a.nch);
+    fwd_pass_b_kernel<<<gb, 256, f.smem, s>>>(a.tmp, a.grid, f.tw, p);
+    TRON_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // namespace tronb

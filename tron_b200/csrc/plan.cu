@@ -1,0 +1,406 @@
+/*
+ * plan.cu -- geometry, plan object and the host pipeline of libtron_b200.
+ *
+ * Replaces the reference's host layer:
+ *   geometry derivation in main()        /root/reference/src/tron.cu:905-961
+ *   tron_init / tron_shutdown            tron.cu:579-620
+ *   tron_nufft_adj_radial2d / _radial2d  tron.cu:623-649
+ *   recon_radial2d (slice loop)          tron.cu:726-786
+ *
+ * Differences in structure (not in results):
+ *   - geometry lives in a plan, not in file-static globals;
+ *   - the acquisition is uploaded ONCE and the sliding window (-d) is addressed
+ *     on the device; the reference re-uploads every overlapping window from
+ *     pageable memory (tron.cu:738-748);
+ *   - slices are processed in batches per launch (3 launches per batch instead
+ *     of 8 per slice), uploads/downloads overlap compute on separate streams;
+ *   - buffers, tables and streams are created once per plan, not per call.
+ */
+#include "tron_internal.h"
+
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+namespace tronb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    return e == cudaErrorMemoryAllocation ? TRON_ENOMEM : TRON_ECUDA;
+}
+
+} // namespace tronb
+
+using namespace tronb;
+
+extern "C" const char *tron_last_error(void) { return tronb::g_err; }
+extern "C" int tron_version(void) { return TRON_B200_VERSION; }
+
+extern "C" void tron_config_defaults(tron_config *c)
+{
+    memset(c, 0, sizeof *c);
+    c->gridos = 2.f; c->kernwidth = 2.f; c->data_undersamp = 1.f;     /* tron.cu:67-69 */
+    c->device = -1;
+}
+
+/* tron.cu:905-961, same int/float conversions and truncations */
+extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
+{
+    memset(g, 0, sizeof *g);
+    if (c->niter != 0) { set_error("-i (CGNR) is not implemented; the reference marks it broken (tron.cu:670)"); return TRON_EUNSUPPORTED; }
+    if (c->koosh) { set_error("-3 (koosh ball) has no kernels in the reference either"); return TRON_EUNSUPPORTED; }
+    if (!(c->gridos > 0.f) || !(c->kernwidth > 0.f) || !(c->data_undersamp > 0.f)) { set_error("gridos, kernwidth and data_undersamp must be positive"); return TRON_EINVAL; }
+    for (int i = 0; i < 5; ++i) if (c->dims[i] == 0 || c->dims[i] > 0x7fffffffULL) { set_error("dims[%d] = %llu out of range", i, (unsigned long long)c->dims[i]); return TRON_EINVAL; }
+    g->nc = (int)c->dims[0]; g->nt = (int)c->dims[1];
+    g->out_dims[0] = 1;                                    /* tron.cu:899 */
+    int slide = c->prof_slide;
+    if (c->adjoint) {
+        g->nro = (int)c->dims[2]; g->npe1 = (int)c->dims[3]; g->npe2 = (int)c->dims[4];
+        g->nx = g->nro / 2; g->ny = g->nro / 2;
+        g->nxos = (int)(g->nx * c->gridos); g->nyos = (int)(g->ny * c->gridos);
+        if ((float)g->npe1 <= (float)g->nro * c->data_undersamp) g->npe1work = g->npe1;
+        else g->npe1work = (int)((float)g->nro * c->data_undersamp);
+        if (g->npe1work < 1) { set_error("npe1work = %d", g->npe1work); return TRON_EINVAL; }
+        if (slide == 0) slide = g->npe1work;
+        if (slide < 0) { set_error("prof_slide must be >= 0"); return TRON_EINVAL; }
+        g->nz = 1 + (g->npe1 - g->npe1work) / slide;
+        g->out_dims[1] = (uint64_t)g->nt; g->out_dims[2] = (uint64_t)g->nx;
+        g->out_dims[3] = (uint64_t)g->ny; g->out_dims[4] = (uint64_t)g->nz;
+        g->in_elems = (uint64_t)g->nc * g->nt * g->nro * g->npe1 * (uint64_t)g->npe2;
+        g->out_elems = (uint64_t)g->nt * g->nx * g->ny * (uint64_t)g->nz;
+    } else {
+        g->nx = (int)c->dims[2]; g->ny = (int)c->dims[3]; g->nz = (int)c->dims[4];
+        g->nxos = (int)(g->nx * c->gridos); g->nyos = (int)(g->ny * c->gridos);
+        g->nro = (int)(c->gridos * g->nx);
+        g->npe1work = (int)(c->data_undersamp * (float)g->nro);
+        g->npe1 = g->npe1work; g->npe2 = 1;              /* prof_slide stays as given (tron.cu:936-961) */
+        g->out_dims[1] = (uint64_t)g->nt; g->out_dims[2] = (uint64_t)g->nro;
+        g->out_dims[3] = (uint64_t)g->npe1; g->out_dims[4] = (uint64_t)g->npe2;
+        g->in_elems = (uint64_t)g->nc * g->nt * g->nx * g->ny * (uint64_t)g->nz;
+        g->out_elems = (uint64_t)g->nc * g->nt * g->nro * g->npe1 * (uint64_t)g->npe2;
+        if (g->nx != g->ny) { set_error("non-square images are not implemented (tron.cu:945)"); return TRON_EUNSUPPORTED; }
+        if (g->nz != 1) { set_error("forward mode with dims[4] = %d: the reference reads every slice from offset 0 and overruns its output (tron.cu:750,776); only dims[4] = 1 is defined", g->nz); return TRON_EUNSUPPORTED; }
+        if (g->npe1work < 1) { set_error("npe1work = %d", g->npe1work); return TRON_EINVAL; }
+    }
+    g->prof_slide = slide;
+    if (!(g->nc % 2 == 0 || g->nc == 1)) { set_error("nc = %d: only a single or an even number of channels (tron.cu:963)", g->nc); return TRON_EINVAL; }
+    if (g->nt != 1) { set_error("nt = %d: the reference builds its FFT plans for nc channels but runs nc*nt (tron.cu:599-601); only nt = 1 is defined", g->nt); return TRON_EUNSUPPORTED; }
+    if (g->nx < 1 || g->nxos < g->nx || (g->nxos & 1)) { set_error("nx = %d, nxos = %d: need an even oversampled grid >= nx", g->nx, g->nxos); return TRON_EINVAL; }
+
+    g->slice_begin = c->slice_begin; g->slice_end = c->slice_end;
+    if (g->slice_begin == 0 && g->slice_end == 0) g->slice_end = c->adjoint ? g->nz : 1;
+    if (!c->adjoint) { g->slice_begin = 0; g->slice_end = 1; }
+    if (g->slice_begin < 0 || g->slice_end > (c->adjoint ? g->nz : 1) || g->slice_begin >= g->slice_end) { set_error("bad slice shard [%d,%d) of %d", g->slice_begin, g->slice_end, g->nz); return TRON_EINVAL; }
+    g->coil_begin = c->coil_begin; g->coil_end = c->coil_end;
+    if (g->coil_begin == 0 && g->coil_end == 0) g->coil_end = g->nc;
+    if (g->coil_begin < 0 || g->coil_end > g->nc || g->coil_begin >= g->coil_end) { set_error("bad coil shard [%d,%d) of %d", g->coil_begin, g->coil_end, g->nc); return TRON_EINVAL; }
+    int nch = g->coil_end - g->coil_begin;
+    if (g->nc > 1 && ((g->coil_begin & 1) || (nch & 1))) { set_error("coil shards must start at an even channel and hold an even count"); return TRON_EINVAL; }
+
+    uint64_t spoke = (uint64_t)g->nc * g->nt * g->nro;
+    if (c->adjoint) {
+        int ns = g->slice_end - g->slice_begin;
+        g->shard_in_offset = spoke * (uint64_t)g->slice_begin * slide;
+        g->shard_in_elems = spoke * ((uint64_t)(ns - 1) * slide + g->npe1work);
+        uint64_t per = (uint64_t)g->nx * g->ny * (c->per_coil_out ? (uint64_t)g->nc : 1);
+        g->shard_out_offset = per * g->slice_begin;
+        g->shard_out_elems = per * ns;
+    } else {
+        g->shard_in_offset = 0; g->shard_in_elems = g->in_elems;
+        g->shard_out_offset = 0; g->shard_out_elems = g->out_elems;
+    }
+    return TRON_OK;
+}
+
+static void plan_release(tron_plan *p)
+{
+    if (!p) return;
+    cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin);
+    fft_plan_free(p->fft);
+    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd);
+    cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_in); cudaFree(p->d_out);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->copy_in) cudaStreamDestroy(p->copy_in);
+    if (p->copy_out) cudaStreamDestroy(p->copy_out);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
+    for (int i = 0; i < 2; ++i) if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+    for (int i = 0; i < 4; ++i) if (p->ev_t[i]) cudaEventDestroy(p->ev_t[i]);
+    delete p;
+}
+
+static int pick_batch(const tron_plan *p)
+{
+    if (p->cfg.batch_slices > 0) return p->cfg.batch_slices < p->nslices ? p->cfg.batch_slices : p->nslices;
+    const char *e = getenv("TRON_BATCH");
+    if (e && atoi(e) > 0) return atoi(e) < p->nslices ? atoi(e) : p->nslices;
+    size_t per = (size_t)p->nch * p->g.nxos * ((size_t)p->g.nxos + p->g.nx) * sizeof(float2);
+    size_t b = ((size_t)192 << 20) / (per ? per : 1);
+    if (b < 1) b = 1;
+    if (b > 32) b = 32;
+    if ((int)b > p->nslices) b = p->nslices;
+    return (int)b;
+}
+
+extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
+{
+    *out = nullptr;
+    tron_geometry g;
+    int rc = tron_geometry_compute(cfg, &g);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        set_error("no CUDA device: libtron_b200 has no CPU path");
+        return TRON_ENODEV;
+    }
+    if (cfg->device >= 0) {
+        if (cfg->device >= ndev) { set_error("device %d of %d", cfg->device, ndev); return TRON_ENODEV; }
+        TRON_CUDA(cudaSetDevice(cfg->device));                       /* -g, tron.cu:837-839 */
+    }
+    tron_plan *p = new tron_plan();
+    p->cfg = *cfg; p->g = g;
+    cudaGetDevice(&p->device);
+    p->nch = g.coil_end - g.coil_begin;
+    p->nslices = g.slice_end - g.slice_begin;
+    p->in_elem_bytes = cfg->half_in ? 4 : 8;
+    p->out_elem_bytes = cfg->half_out ? 4 : 8;
+    if (cfg->adjoint && cfg->sos_partial && g.nc > 1) p->out_elem_bytes = 4;
+    p->in_bytes = g.shard_in_elems * p->in_elem_bytes;
+    p->out_bytes = g.shard_out_elems * p->out_elem_bytes;
+
+#define PLAN_TRY(call) do { int rc__ = (call); if (rc__) { plan_release(p); return rc__; } } while (0)
+#define PLAN_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+        int rc__ = cuda_fail(e__, #call, __FILE__, __LINE__); plan_release(p); return rc__; } } while (0)
+
+    PLAN_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PLAN_CUDA(cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking));
+    PLAN_CUDA(cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking));
+    PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) PLAN_CUDA(cudaEventCreate(&p->ev_t[i]));
+
+    const int n = g.nxos;
+    if (cfg->adjoint) {
+        int ntab = cfg->golden_angle ? p->nslices : 1;
+        int skip = cfg->skip_angles + (cfg->golden_angle ? g.slice_begin * g.prof_slide : 0);
+        PLAN_TRY(launch_build_tables(p->tabs, g.npe1work, ntab, g.prof_slide, skip, cfg->golden_angle, 1, p->stream));
+    } else {
+        PLAN_TRY(launch_build_tables(p->tabs, g.npe1work, 1, 0, cfg->skip_angles, cfg->golden_angle, 0, p->stream));
+    }
+    PLAN_TRY(fft_plan_init(p->fft, n, g.nx));
+    PLAN_CUDA(cudaMalloc(&p->deapod_adj, (size_t)g.nx * g.nx * sizeof(float)));
+    PLAN_CUDA(cudaMalloc(&p->deapod_fwd, (size_t)g.nx * g.nx * sizeof(float)));
+    PLAN_TRY(launch_deapod_tables(p->deapod_adj, p->deapod_fwd, g.nx, n, cfg->kernwidth, cfg->gridos, p->stream));
+
+    p->batch = cfg->adjoint ? pick_batch(p) : 1;
+    PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)p->batch * p->nch * n * n * sizeof(float2)));
+    PLAN_CUDA(cudaMalloc(&p->d_tmp, (size_t)p->batch * p->nch * n * g.nx * sizeof(float2)));
+    PLAN_CUDA(cudaStreamSynchronize(p->stream));
+#undef PLAN_TRY
+#undef PLAN_CUDA
+    *out = p;
+    return TRON_OK;
+}
+
+extern "C" int tron_plan_destroy(tron_plan *p)
+{
+    if (!p) return TRON_OK;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    plan_release(p);
+    return TRON_OK;
+}
+
+extern "C" int tron_plan_geometry(const tron_plan *p, tron_geometry *g)
+{
+    if (!p || !g) { set_error("null plan"); return TRON_EINVAL; }
+    *g = p->g;
+    return TRON_OK;
+}
+
+static GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d_grid, int z0, int nb)
+{
+    const tron_geometry &g = p->g;
+    GridLaunch L;
+    L.samples = d_samples; L.grid = d_grid;
+    L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.lut = p->tabs.lut;
+    L.tab_per_slice = p->tabs.ntab > 1 ? 1 : 0;
+    L.nbins = p->tabs.nbins;
+    L.n = g.nxos; L.nro = g.nro; L.npe = g.npe1work;
+    L.nc_total = g.nc * g.nt; L.ch0 = g.coil_begin; L.nch = p->nch;
+    L.z0 = z0; L.nslices = nb; L.slide = g.prof_slide;
+    L.kb = make_kb(p->cfg.kernwidth);
+    /* tron.cu:408-409 and 532 */
+    L.sdc_a = (2.f - 2.f / (float)g.npe1work) / (float)g.nro;
+    L.sdc_b = 1.f / (float)g.npe1work;
+    L.scale = 1.f / (float)g.nxos / (float)g.npe1work;
+    L.half_in = p->cfg.half_in;
+    return L;
+}
+
+static int adjoint_mode(const tron_plan *p)
+{
+    if (p->cfg.per_coil_out) return 2;
+    if (p->g.nc == 1) return 1;                      /* tron.cu:265-266 */
+    return p->cfg.sos_partial ? 3 : 0;
+}
+
+/* one batch of adjoint slices, all on stream s */
+static int run_adjoint_batch(tron_plan *p, void *d_out, const void *d_in, int z0, int nb, cudaStream_t s)
+{
+    const tron_geometry &g = p->g;
+    GridLaunch L = make_grid_launch(p, d_in, p->d_grid, z0, nb);
+    int rc = launch_grid(L, s);
+    if (rc) return rc;
+    AdjFftLaunch a;
+    a.grid = p->d_grid; a.tmp = p->d_tmp; a.deapod = p->deapod_adj;
+    a.nslices = nb; a.nch = p->nch; a.nc_total = g.nc * g.nt; a.ch0 = g.coil_begin;
+    a.mode = adjoint_mode(p); a.half_out = p->cfg.half_out;
+    size_t per = (size_t)g.nx * g.ny * (a.mode == 2 ? (size_t)g.nc : 1);
+    a.out = (char *)d_out + (size_t)z0 * per * p->out_elem_bytes;
+    rc = launch_adj_fft(p->fft, a, s);
+    p->last_launches += 3;
+    return rc;
+}
+
+static int run_forward(tron_plan *p, void *d_out, const void *d_in, cudaStream_t s)
+{
+    const tron_geometry &g = p->g;
+    FwdFftLaunch f;
+    f.img = d_in; f.tmp = p->d_tmp; f.grid = p->d_grid; f.deapod = p->deapod_fwd;
+    f.nch = p->nch; f.nc_total = g.nc * g.nt; f.ch0 = g.coil_begin; f.half_in = p->cfg.half_in;
+    int rc = launch_fwd_fft(p->fft, f, s);
+    if (rc) return rc;
+    DegridLaunch d;
+    d.samples = d_out; d.grid = p->d_grid; d.cs = p->tabs.cs_lin;
+    d.n = g.nxos; d.nro = g.nro; d.npe = g.npe1work;
+    d.nc_total = g.nc * g.nt; d.ch0 = g.coil_begin; d.nch = p->nch;
+    d.kb = make_kb(p->cfg.kernwidth); d.half_out = p->cfg.half_out;
+    rc = launch_degrid(d, s);
+    p->last_launches += 3;
+    return rc;
+}
+
+extern "C" int tron_recon_device(tron_plan *p, void *d_out, const void *d_in, void *stream)
+{
+    if (!p || !d_out || !d_in) { set_error("null argument"); return TRON_EINVAL; }
+    TRON_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    p->last_launches = 0;
+    if (!p->cfg.adjoint) return run_forward(p, d_out, d_in, s);
+    for (int z0 = 0; z0 < p->nslices; z0 += p->batch) {
+        int nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
+        int rc = run_adjoint_batch(p, d_out, d_in, z0, nb, s);
+        if (rc) return rc;
+    }
+    return TRON_OK;
+}
+
+extern "C" int tron_recon_host(tron_plan *p, void *h_out, const void *h_in)
+{
+    if (!p || !h_out || !h_in) { set_error("null argument"); return TRON_EINVAL; }
+    TRON_CUDA(cudaSetDevice(p->device));
+    if (!p->d_in) TRON_CUDA(cudaMalloc(&p->d_in, p->in_bytes));
+    if (!p->d_out) TRON_CUDA(cudaMalloc(&p->d_out, p->out_bytes));
+    p->last_launches = 0;
+    const tron_geometry &g = p->g;
+    if (!p->cfg.adjoint) {
+        TRON_CUDA(cudaMemcpyAsync(p->d_in, h_in, p->in_bytes, cudaMemcpyHostToDevice, p->stream));
+        int rc = run_forward(p, p->d_out, p->d_in, p->stream);
+        if (rc) return rc;
+        TRON_CUDA(cudaMemcpyAsync(h_out, p->d_out, p->out_bytes, cudaMemcpyDeviceToHost, p->stream));
+        TRON_CUDA(cudaStreamSynchronize(p->stream));
+        return TRON_OK;
+    }
+    /* adjoint: upload each spoke once, in the order the batches need them;
+     * compute waits for its window; downloads trail the compute stream */
+    const size_t spoke_bytes = (size_t)g.nc * g.nt * g.nro * p->in_elem_bytes;
+    const size_t slice_out_bytes = (size_t)g.nx * g.ny * (p->cfg.per_coil_out ? (size_t)g.nc : 1) * p->out_elem_bytes;
+    size_t spokes_up = 0;
+    int parity = 0;
+    for (int z0 = 0; z0 < p->nslices; z0 += p->batch, parity ^= 1) {
+        int nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
+        size_t need = (size_t)(z0 + nb - 1) * g.prof_slide + g.npe1work;
+        if (need > spokes_up) {
+            TRON_CUDA(cudaMemcpyAsync((char *)p->d_in + spokes_up * spoke_bytes,
+                                      (const char *)h_in + spokes_up * spoke_bytes,
+                                      (need - spokes_up) * spoke_bytes, cudaMemcpyHostToDevice, p->copy_in));
+            spokes_up = need;
+            TRON_CUDA(cudaEventRecord(p->ev_in, p->copy_in));
+            TRON_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in, 0));
+        }
+        int rc = run_adjoint_batch(p, p->d_out, p->d_in, z0, nb, p->stream);
+        if (rc) return rc;
+        TRON_CUDA(cudaEventRecord(p->ev_done[parity], p->stream));
+        TRON_CUDA(cudaStreamWaitEvent(p->copy_out, p->ev_done[parity], 0));
+        TRON_CUDA(cudaMemcpyAsync((char *)h_out + (size_t)z0 * slice_out_bytes,
+                                  (char *)p->d_out + (size_t)z0 * slice_out_bytes,
+                                  (size_t)nb * slice_out_bytes, cudaMemcpyDeviceToHost, p->copy_out));
+    }
+    TRON_CUDA(cudaStreamSynchronize(p->copy_out));
+    TRON_CUDA(cudaStreamSynchronize(p->stream));
+    return TRON_OK;
+}
+
+/* ---------------- stage-level entry points ---------------- */
+extern "C" int tron_grid_device(tron_plan *p, void *d_grid, const void *d_samples, int z0, int nslices, void *stream)
+{
+    if (!p || !p->cfg.adjoint) { set_error("tron_grid_device needs an adjoint plan"); return TRON_EINVAL; }
+    if (z0 < 0 || nslices < 1 || z0 + nslices > p->nslices) { set_error("slice range [%d,%d) outside the plan's %d slices", z0, z0 + nslices, p->nslices); return TRON_EINVAL; }
+    TRON_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    GridLaunch L = make_grid_launch(p, d_samples, (float2 *)d_grid, z0, nslices);
+    return launch_grid(L, s);
+}
+
+extern "C" int tron_grid_to_interleaved(tron_plan *p, void *d_dst, const void *d_grid, int nslices, void *stream)
+{
+    if (!p) { set_error("null plan"); return TRON_EINVAL; }
+    TRON_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    return launch_interleave((float2 *)d_dst, (const float2 *)d_grid, p->nch, p->g.nxos, nslices, s);
+}
+
+extern "C" int tron_degrid_device(tron_plan *p, void *d_samples, const void *d_grid, void *stream)
+{
+    if (!p || p->cfg.adjoint) { set_error("tron_degrid_device needs a forward plan"); return TRON_EINVAL; }
+    TRON_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const tron_geometry &g = p->g;
+    if (p->nch != g.nc) { set_error("tron_degrid_device does not support coil shards"); return TRON_EUNSUPPORTED; }
+    int rc = launch_deinterleave(p->d_grid, (const float2 *)d_grid, p->nch, g.nxos, s);
+    if (rc) return rc;
+    DegridLaunch d;
+    d.samples = d_samples; d.grid = p->d_grid; d.cs = p->tabs.cs_lin;
+    d.n = g.nxos; d.nro = g.nro; d.npe = g.npe1work;
+    d.nc_total = g.nc * g.nt; d.ch0 = 0; d.nch = p->nch;
+    d.kb = make_kb(p->cfg.kernwidth); d.half_out = p->cfg.half_out;
+    return launch_degrid(d, s);
+}
+
+extern "C" int tron_plan_last_stage_ms(tron_plan *p, float ms[3])
+{
+    if (!p) { set_error("null plan"); return TRON_EINVAL; }
+    for (int i = 0; i < 3; ++i) ms[i] = p->last_ms[i];
+    return TRON_OK;
+}
+
+extern "C" int tron_plan_last_launches(const tron_plan *p) { return p ? p->last_launches : 0; }
+
+/* pinned host memory for ra_read_pinned (ra.c is plain C and does not see cudart) */
+extern "C" int tron_pinned_alloc(void **p, size_t bytes)
+{
+    return cudaMallocHost(p, bytes) == cudaSuccess ? 0 : -1;
+}
+extern "C" void tron_pinned_free(void *p) { if (p) cudaFreeHost(p); }

@@ -1,0 +1,113 @@
+/* tron_internal.h -- plan object and kernel launch interfaces (not installed). */
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/tron.h"
+#include "refmath.cuh"
+
+namespace tronb {
+
+void set_error(const char *fmt, ...);
+int  cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define TRON_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+    return tronb::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
+
+/* One sorted-spoke table per slice (golden angle) or one shared table (linear). */
+struct SpokeTables {
+    float4 *cs = nullptr;     /* [ntab][npe]  (cos, sin, 1/cos, 1/sin), sorted by angle mod pi */
+    int    *pe = nullptr;     /* [ntab][npe]  window-relative spoke index of each sorted entry */
+    int    *lut = nullptr;    /* [ntab][nbins+1] first sorted entry of each angular bin */
+    float2 *cs_lin = nullptr; /* [ntab][npe]  (cos, sin) in acquisition order (degridding) */
+    int ntab = 0, nbins = 0;
+};
+
+struct GridLaunch {               /* everything the gridding kernel needs */
+    const void *samples;          /* first spoke of shard-local slice 0 */
+    float2 *grid;                 /* [nslices][nch][n][n] */
+    const float4 *tab_cs; const int *tab_pe; const int *lut;
+    int tab_per_slice;            /* 1: table index = slice, 0: shared */
+    int nbins;
+    int n, nro, npe, nc_total, ch0, nch;
+    int z0, nslices, slide;
+    KbParams kb;
+    float sdc_a, sdc_b, scale;
+    int half_in;
+};
+
+struct DegridLaunch {
+    void *samples;                /* [npe][nro][nc_total] */
+    const float2 *grid;           /* planar [nch][n][n] */
+    const float2 *cs;             /* [npe] (cos, sin) acquisition order */
+    int n, nro, npe, nc_total, ch0, nch;
+    KbParams kb;
+    int half_out;
+};
+
+int launch_grid(const GridLaunch &g, cudaStream_t s);
+int launch_degrid(const DegridLaunch &d, cudaStream_t s);
+int launch_build_tables(SpokeTables &t, int npe, int nslices_tab, int slide, int skip, int golden,
+                        int adjoint, cudaStream_t s);
+int launch_interleave(float2 *dst, const float2 *planar, int nch, int n, int nslices, cudaStream_t s);
+int launch_deinterleave(float2 *planar, const float2 *src, int nch, int n, cudaStream_t s);
+
+/* FFT stage */
+struct FftPlan {
+    int n = 0;                    /* transform length (nxos) */
+    int nkeep = 0;                /* nx */
+    int nfac = 0; int fac[16];    /* radix schedule */
+    float2 *tw = nullptr;         /* [n] exp(+2 pi i k / n) */
+    int lines = 0;                /* lines per CTA */
+    size_t smem = 0;
+};
+int fft_plan_init(FftPlan &f, int n, int nkeep);
+void fft_plan_free(FftPlan &f);
+
+struct AdjFftLaunch {
+    const float2 *grid;           /* planar [nslices][nch][n][n] */
+    float2 *tmp;                  /* [nslices][nch][nkeep][n] */
+    void *out;                    /* see mode */
+    const float *deapod;          /* [nkeep][nkeep] reciprocal weights */
+    int nslices, nch, nc_total, ch0;
+    int mode;                     /* 0 rss (complex64 out), 1 single-channel complex, 2 per-coil interleaved,
+                                     3 partial sum of squares (float) */
+    int half_out;
+};
+int launch_adj_fft(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s);
+
+struct FwdFftLaunch {
+    const void *img;              /* [nx][nx][nc_total] channel-interleaved */
+    float2 *tmp;                  /* [nch][n][nkeep] */
+    float2 *grid;                 /* planar [nch][n][n] */
+    const float *deapod;          /* [nkeep][nkeep] reciprocal weights of the padded region */
+    int nch, nc_total, ch0;
+    int half_in;
+};
+int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s);
+int launch_deapod_tables(float *adj_tab, float *fwd_tab, int nx, int nxos, float W, float gridos, cudaStream_t s);
+
+} // namespace tronb
+
+struct tron_plan {
+    tron_config cfg;
+    tron_geometry g;
+    int device = 0;
+    int nch = 0;                         /* channels this plan owns */
+    int nslices = 0;                     /* slices this plan owns */
+    int batch = 1;
+    cudaStream_t stream = nullptr;       /* compute */
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done[2] = {nullptr, nullptr}, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    tronb::SpokeTables tabs;
+    tronb::FftPlan fft;
+    float *deapod_adj = nullptr, *deapod_fwd = nullptr;
+    float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
+    void *d_in = nullptr, *d_out = nullptr;         /* device staging for the host API */
+    size_t in_bytes = 0, out_bytes = 0;
+    size_t in_elem_bytes = 8, out_elem_bytes = 8;
+    int last_launches = 0;
+    float last_ms[3] = {0, 0, 0};
+};
