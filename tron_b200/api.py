@@ -266,6 +266,13 @@ class Plan:
     def last_launches(self):
         return int(self.lib.tron_plan_last_launches(self.handle))
 
+    def last_stage_ms(self):
+        """(gridding/degridding, FFT passes, other) device ms of the last recon_device call;
+        only filled when the plan was created with TRON_STAGE_TIMING set (diagnostic mode)."""
+        ms = (C.c_float * 3)()
+        _check(self.lib.tron_plan_last_stage_ms(self.handle, ms), self.lib)
+        return [float(x) for x in ms]
+
 
 def recon_radial2d(h_in, dims, **flags):
     """One-shot equivalent of `tron [flags] in.ra out.ra` on arrays: returns (output, out_dims)."""

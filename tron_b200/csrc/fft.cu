@@ -31,6 +31,7 @@
  */
 #include "tron_internal.h"
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace tronb {
@@ -46,8 +47,8 @@ __device__ __forceinline__ float2 cmuli(float2 a, float s) { return make_float2(
 
 /* shared-memory index padding: one extra element every 8 keeps the strided
  * Stockham accesses (stride = radix) off a single bank */
-__device__ __forceinline__ int phys(int i) { return i + (i >> 3); }
-static inline int phys_host(int i) { return i + (i >> 3); }
+__device__ __forceinline__ int phys(int i) { return i + (i >> 4); }
+static inline int phys_host(int i) { return i + (i >> 4); }
 
 template <int R> struct Dft;
 template <> struct Dft<2> {
@@ -332,6 +333,315 @@ fwd_pass_b_kernel(const float2 *__restrict__ tmp, float2 *__restrict__ grid, con
     }
 }
 
+/* ====================================================================== */
+/* power-of-two fast path: radix-8 butterflies in registers               */
+/* ====================================================================== */
+/*
+ * One line of N points is owned by N/8 threads; thread j holds elements
+ * j + q*N/8 (q = 0..7) in registers.  Every Stockham stage is: butterflies in
+ * registers -> scatter to shared memory (autosort index) -> barrier -> gather
+ * j + q*N/8 again.  Two shared buffers alternate, so one barrier per stage.
+ * All index arithmetic is compile-time shifts and masks.
+ */
+template <int N, int L> struct P2 {
+    static constexpr int T = N / 8;                 /* threads per line */
+    /* line pitch: >= phys(N-1)+1 and == 16/L (mod 16), so that the transposed read of the
+     * store phase (L lines x 16/L consecutive outputs per half-warp) hits 16 distinct bank pairs */
+    static constexpr int BASE = N + N / 16;
+    static constexpr int WANT = L >= 16 ? 1 : 16 / L;
+    static constexpr int PITCH = BASE + ((WANT - BASE % 16) + 16) % 16 + (((WANT - BASE % 16) + 16) % 16 == 0 ? 16 : 0);
+};
+
+template <int N, int Ns, int R, int SGN>
+__device__ __forceinline__ void p2_stage(float2 (&v)[8], float2 *dst, const float2 *stw, int j)
+{
+    constexpr int T = N / 8, M = 8 / R, TSTEP = N / (Ns * R);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int b = j + m * T;
+        const int k = b & (Ns - 1);
+        float2 x[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) x[t] = v[m + t * M];
+        if (Ns > 1) {
+            /* w^t from one table read and a depth-3 product chain: the strided reads
+             * stw[t*k*TSTEP] serialise on shared-memory banks */
+            float2 w1 = stw[phys(k * TSTEP)];
+            if (SGN < 0) w1.y = -w1.y;
+            x[1] = cmul(x[1], w1);
+            if constexpr (R > 2) {
+                const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                x[2] = cmul(x[2], w2); x[3] = cmul(x[3], w3);
+                if constexpr (R > 4) {
+                    const float2 w4 = cmul(w2, w2);
+                    x[4] = cmul(x[4], w4); x[5] = cmul(x[5], cmul(w4, w1));
+                    x[6] = cmul(x[6], cmul(w3, w3)); x[7] = cmul(x[7], cmul(w4, w3));
+                }
+            }
+        }
+        Dft<R>::run(x, (float)SGN);
+        const int j0 = (b - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; ++t) dst[phys(j0 + t * Ns)] = x[t];
+    }
+}
+
+template <int N, int Ns, int SGN>
+__device__ __forceinline__ void p2_stages(float2 (&v)[8], float2 *bufA, float2 *bufB, const float2 *stw, int j)
+{
+    constexpr int REM = N / Ns;
+    constexpr int R = REM >= 8 ? 8 : REM;
+    p2_stage<N, Ns, R, SGN>(v, bufA, stw, j);
+    __syncthreads();
+    if constexpr (Ns * R < N) {
+        constexpr int T = N / 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = bufA[phys(j + q * T)];
+        p2_stages<N, Ns * R, SGN>(v, bufB, bufA, stw, j);
+    }
+}
+
+/* number of stages decides which buffer holds the natural-order result */
+template <int N> __host__ __device__ constexpr int p2_nstages() { int s = 0, m = N; while (m > 1) { m = m >= 8 ? m / 8 : 1; ++s; } return s; }
+
+/* Transform: registers in (element j + q*T of the line), result in shared memory, natural order.
+ * Returns the line base inside the result buffer.  lineA/lineB are this line's two buffers. */
+template <int N, int SGN>
+__device__ __forceinline__ float2 *p2_fft(float2 (&v)[8], float2 *lineA, float2 *lineB, const float2 *stw, int j)
+{
+    p2_stages<N, 1, SGN>(v, lineA, lineB, stw, j);
+    return (p2_nstages<N>() & 1) ? lineA : lineB;
+}
+
+template <int N, int L>
+__global__ void __launch_bounds__(L *(N / 8))
+p2_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep)
+{
+    extern __shared__ float2 smem[];
+    constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
+    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
+    const int l = threadIdx.x / T, j = threadIdx.x % T;
+    const int y0 = blockIdx.x * L;
+    const size_t plane = blockIdx.y;
+    for (int i = threadIdx.x; i < N; i += L * T) stw[phys(i)] = tw[i];
+    const float2 *g = grid + plane * (size_t)N * N + (size_t)(y0 + l) * N;
+    float2 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = g[j + q * T];
+    __syncthreads();
+    float2 *res = p2_fft<N, +1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j) - l * PITCH;
+    const int w = (N - nkeep) / 2, h = N / 2;
+    float2 *out = tmp + plane * (size_t)nkeep * N + y0;
+    for (int idx = threadIdx.x; idx < nkeep * L; idx += L * T) {
+        const int b = idx / L, ll = idx % L;
+        const int k = (b + w - h) & (N - 1);
+        float2 val = res[ll * PITCH + phys(k)];
+        if (k & 1) { val.x = -val.x; val.y = -val.y; }
+        out[(size_t)b * N + ll] = val;
+    }
+}
+
+template <int N, int L, int OUTS>
+__global__ void __launch_bounds__(L *(N / 8), (L * (N / 8) <= 256 ? 3 : 1))
+p2_adj_pass_b(const float2 *__restrict__ tmp, void *__restrict__ outv, const float *__restrict__ deapod,
+              const float2 *__restrict__ tw, int nkeep, int nch, int nc_total, int ch0, int mode, int half_out)
+{
+    extern __shared__ float2 smem[];
+    constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
+    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
+    const int l = threadIdx.x / T, j = threadIdx.x % T;
+    const int b0 = blockIdx.x * L;
+    const int slice = blockIdx.y;
+    const int w = (N - nkeep) / 2, h = N / 2;
+    for (int i = threadIdx.x; i < N; i += L * T) stw[phys(i)] = tw[i];
+    float acc[OUTS];
+#pragma unroll
+    for (int o = 0; o < OUTS; ++o) acc[o] = 0.f;
+    const size_t img = (size_t)nkeep * nkeep;
+    const bool line_ok = b0 + l < nkeep;
+    const size_t chan_stride = (size_t)nkeep * N;
+    const float2 *src = tmp + ((size_t)slice * nch * nkeep + b0 + l) * (size_t)N + j;
+
+    /* software pipeline over the coils: the next coil's line is in flight while this one is transformed */
+    float2 v[8], nv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = line_ok ? src[q * T] : make_float2(0.f, 0.f);
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) nv[q] = line_ok ? src[(size_t)(ch + 1) * chan_stride + q * T] : make_float2(0.f, 0.f);
+        }
+        __syncthreads();                     /* previous coil's epilogue reads are done */
+        float2 *res = p2_fft<N, +1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j) - l * PITCH;
+#pragma unroll
+        for (int o = 0; o < OUTS; ++o) {
+            const int idx = threadIdx.x + o * (L * T);
+            const int a = idx / L, ll = idx % L;
+            if (a < nkeep && b0 + ll < nkeep) {
+                const int k = (a + w - h) & (N - 1);
+                float2 val = res[ll * PITCH + phys(k)];
+                float s = __ldg(deapod + (size_t)a * nkeep + b0 + ll);
+                if (k & 1) s = -s;
+                val.x *= s; val.y *= s;
+                const size_t pix = (size_t)a * nkeep + b0 + ll;
+                if (mode == 0 || mode == 3) acc[o] += val.x * val.x + val.y * val.y;
+                else if (mode == 1) {
+                    if (half_out) ((__half2 *)outv)[(size_t)slice * img + pix] = __float22half2_rn(val);
+                    else ((float2 *)outv)[(size_t)slice * img + pix] = val;
+                } else {
+                    const size_t o2 = ((size_t)slice * img + pix) * nc_total + ch0 + ch;
+                    if (half_out) ((__half2 *)outv)[o2] = __float22half2_rn(val);
+                    else ((float2 *)outv)[o2] = val;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = nv[q];
+    }
+    if (mode == 0 || mode == 3) {
+#pragma unroll
+        for (int o = 0; o < OUTS; ++o) {
+            const int idx = threadIdx.x + o * (L * T);
+            const int a = idx / L, ll = idx % L;
+            if (a < nkeep && b0 + ll < nkeep) {
+                const size_t pix = (size_t)slice * img + (size_t)a * nkeep + b0 + ll;
+                if (mode == 3) ((float *)outv)[pix] = acc[o];
+                else {
+                    float2 val = make_float2(sqrtf(acc[o]), 0.f);      /* tron.cu:263-264 */
+                    if (half_out) ((__half2 *)outv)[pix] = __float22half2_rn(val);
+                    else ((float2 *)outv)[pix] = val;
+                }
+            }
+        }
+    }
+}
+
+template <int N, int L>
+__global__ void __launch_bounds__(L *(N / 8))
+p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const float *__restrict__ deapod,
+              const float2 *__restrict__ tw, int nx, int nc_total, int ch0, int half_in)
+{
+    extern __shared__ float2 smem[];
+    constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
+    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
+    const int l = threadIdx.x / T, j = threadIdx.x % T;
+    const int a = blockIdx.x * L + l;
+    const int ch = blockIdx.y;
+    const int w = (N - nx) / 2, h = N / 2;
+    for (int i = threadIdx.x; i < N; i += L * T) stw[phys(i)] = tw[i];
+    float2 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int b = j + q * T - w;                 /* source column of padded column j + q*T */
+        v[q] = make_float2(0.f, 0.f);
+        if (a >= 1 && a < nx && b >= 1 && b < nx) {  /* pad drops row 0 and column 0, tron.cu:449-450 */
+            const size_t e = ((size_t)a * nx + b) * nc_total + ch0 + ch;
+            float2 x = half_in ? __half22float2(((const __half2 *)imgv)[e]) : ((const float2 *)imgv)[e];
+            const float s = __ldg(deapod + (size_t)a * nx + b);
+            v[q] = make_float2(x.x * s, x.y * s);
+        }
+    }
+    __syncthreads();
+    float2 *res = p2_fft<N, -1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j) - l * PITCH;
+    const int a0 = blockIdx.x * L;
+    float2 *out = tmp + (size_t)ch * N * nx + a0;
+    for (int idx = threadIdx.x; idx < N * L; idx += L * T) {
+        const int c = idx / L, ll = idx % L;
+        const int k = (c + h) & (N - 1);
+        float2 val = res[ll * PITCH + phys(k)];
+        if (k & 1) { val.x = -val.x; val.y = -val.y; }
+        if (a0 + ll < nx) out[(size_t)c * nx + ll] = val;
+    }
+}
+
+template <int N, int L>
+__global__ void __launch_bounds__(L *(N / 8))
+p2_fwd_pass_b(const float2 *__restrict__ tmp, float2 *__restrict__ grid, const float2 *__restrict__ tw, int nx)
+{
+    extern __shared__ float2 smem[];
+    constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
+    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
+    const int l = threadIdx.x / T, j = threadIdx.x % T;
+    const int c0 = blockIdx.x * L;
+    const int ch = blockIdx.y;
+    const int w = (N - nx) / 2, h = N / 2;
+    for (int i = threadIdx.x; i < N; i += L * T) stw[phys(i)] = tw[i];
+    const float2 *src = tmp + ((size_t)ch * N + c0 + l) * nx;
+    float2 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int a = j + q * T - w;
+        v[q] = (a >= 0 && a < nx) ? src[a] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    float2 *res = p2_fft<N, -1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j) - l * PITCH;
+    float2 *out = grid + (size_t)ch * N * N + c0;
+    for (int idx = threadIdx.x; idx < N * L; idx += L * T) {
+        const int r = idx / L, ll = idx % L;
+        const int k = (r + h) & (N - 1);
+        float2 val = res[ll * PITCH + phys(k)];
+        if (k & 1) { val.x = -val.x; val.y = -val.y; }
+        out[(size_t)r * N + ll] = val;
+    }
+}
+
+template <int N, int L> struct P2Launch {
+    static constexpr size_t SMEM = (size_t)(2 * L * P2<N, L>::PITCH + N + N / 8 + 1) * sizeof(float2);
+    static constexpr int THREADS = L * (N / 8);
+    static int prepare()
+    {
+        TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_a<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_b<N, L, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_b<N, L, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TRON_CUDA(cudaFuncSetAttribute(p2_fwd_pass_a<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TRON_CUDA(cudaFuncSetAttribute(p2_fwd_pass_b<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        return 0;
+    }
+    static int adj(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
+    {
+        dim3 ga(N / L, a.nslices * a.nch);
+        p2_adj_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.grid, a.tmp, f.tw, f.nkeep);
+        TRON_CUDA(cudaGetLastError());
+        dim3 gb((f.nkeep + L - 1) / L, a.nslices);
+        if (2 * f.nkeep <= N)
+            p2_adj_pass_b<N, L, 4><<<gb, THREADS, SMEM, s>>>(a.tmp, a.out, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total,
+                                                             a.ch0, a.mode, a.half_out);
+        else
+            p2_adj_pass_b<N, L, 8><<<gb, THREADS, SMEM, s>>>(a.tmp, a.out, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total,
+                                                             a.ch0, a.mode, a.half_out);
+        TRON_CUDA(cudaGetLastError());
+        return 0;
+    }
+    static int fwd(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)
+    {
+        dim3 ga((f.nkeep + L - 1) / L, a.nch);
+        p2_fwd_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.img, a.tmp, a.deapod, f.tw, f.nkeep, a.nc_total, a.ch0, a.half_in);
+        TRON_CUDA(cudaGetLastError());
+        dim3 gb(N / L, a.nch);
+        p2_fwd_pass_b<N, L><<<gb, THREADS, SMEM, s>>>(a.tmp, a.grid, f.tw, f.nkeep);
+        TRON_CUDA(cudaGetLastError());
+        return 0;
+    }
+};
+
+/* lines per CTA chosen so that a CTA has 256..512 threads */
+#define P2_DISPATCH(n, CALL)                                   \
+    switch (n) {                                               \
+    case 64:   return P2Launch<64, 16>::CALL;                  \
+    case 128:  return P2Launch<128, 16>::CALL;                 \
+    case 256:  return P2Launch<256, 8>::CALL;                  \
+    case 512:  return P2Launch<512, 4>::CALL;                  \
+    case 1024: return P2Launch<1024, 4>::CALL;                 \
+    case 2048: return P2Launch<2048, 2>::CALL;                 \
+    case 4096: return P2Launch<4096, 1>::CALL;                 \
+    default: break;                                            \
+    }
+
+static bool is_p2(int n) { return n >= 64 && n <= 4096 && (n & (n - 1)) == 0; }
+static int p2_prepare(int n) { P2_DISPATCH(n, prepare()) return 0; }
+static int p2_adj(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s) { P2_DISPATCH(f.n, adj(f, a, s)) return TRON_EUNSUPPORTED; }
+static int p2_fwd(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s) { P2_DISPATCH(f.n, fwd(f, a, s)) return TRON_EUNSUPPORTED; }
+
 /* ------- deapodisation tables (reciprocal weights), tron.cu:351-370, 390-402 ------- */
 __device__ __forceinline__ float kb_hat(float u, float kernwidth)
 {
@@ -417,6 +727,7 @@ int fft_plan_init(FftPlan &f, int n, int nkeep)
     }
     TRON_CUDA(cudaMalloc(&f.tw, n * sizeof(float2)));
     TRON_CUDA(cudaMemcpy(f.tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    if (is_p2(n) && !getenv("TRON_GENERIC_FFT")) { int rc = p2_prepare(n); if (rc) return rc; f.pow2 = 1; }
     TRON_CUDA(cudaFuncSetAttribute(adj_pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem));
     TRON_CUDA(cudaFuncSetAttribute(adj_pass_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem));
     TRON_CUDA(cudaFuncSetAttribute(fwd_pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem));
@@ -432,6 +743,7 @@ void fft_plan_free(FftPlan &f)
 
 int launch_adj_fft(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
 {
+    if (f.pow2) return p2_adj(f, a, s);
     PassGeom p = make_geom(f);
     dim3 ga((f.n + p.L - 1) / p.L, a.nslices * a.nch);
     adj_pass_a_kernel<<<ga, 256, f.smem, s>>>(a.grid, a.tmp, f.tw, p);
@@ -445,6 +757,7 @@ int launch_adj_fft(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
 
 int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)
 {
+    if (f.pow2) return p2_fwd(f, a, s);
     PassGeom p = make_geom(f);
     dim3 ga((f.nkeep + p.L - 1) / p.L, a.nch);
     fwd_pass_a_kernel<<<ga, 256, f.smem, s>>>(a.img, a.tmp, a.deapod, f.tw, p, a.nc_total, a.ch0, a.half_in);

@@ -32,6 +32,10 @@
  * Output is planar: grid[slice][ch][row][col].
  */
 #include "tron_internal.h"
+#include <algorithm>
+#include <math.h>
+#include <utility>
+#include <vector>
 
 namespace tronb {
 
@@ -92,6 +96,55 @@ __global__ void spoke_table_kernel(float4 *cs, int *pe_sorted, int *lut, float2 
         }
         l[b] = lo;
     }
+}
+
+/* tiles of 16x16 cells ordered by the distance of their nearest cell from DC */
+int build_tile_order(int **d_order, int n)
+{
+    int tx = (n + 15) / 16, nt = tx * tx;
+    std::vector<std::pair<float, int>> key(nt);
+    for (int t = 0; t < nt; ++t) {
+        int x0 = (t % tx) * 16 - n / 2, y0 = (t / tx) * 16 - n / 2;
+        float dx = x0 > 0 ? (float)x0 : (x0 + 15 < 0 ? (float)-(x0 + 15) : 0.f);
+        float dy = y0 > 0 ? (float)y0 : (y0 + 15 < 0 ? (float)-(y0 + 15) : 0.f);
+        key[t] = std::make_pair(dx * dx + dy * dy, t);
+    }
+    std::sort(key.begin(), key.end());
+    std::vector<int> order(nt);
+    for (int t = 0; t < nt; ++t) order[t] = key[t].second;
+    TRON_CUDA(cudaMalloc(d_order, nt * sizeof(int)));
+    TRON_CUDA(cudaMemcpy(*d_order, order.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+/* Cells with X^2 + Y^2 <= r2 are "heavy": their spoke window holds about
+ * HEAVY_SPOKES or more spokes.  Returns the list (packed y<<16 | x, nearest DC first). */
+int build_heavy_cells(int **d_cells, int *nheavy, int *heavy_r2, int n, int npe, float W)
+{
+    const int HEAVY_SPOKES = 24;
+    *d_cells = nullptr; *nheavy = 0; *heavy_r2 = -1;
+    double arg = HEAVY_SPOKES * 3.14159265358979323846 / (2.0 * npe);
+    if (arg >= 1.2) return 0;                              /* too few spokes for any cell to be heavy */
+    double reach = (double)W * 1.41421368 + 2e-3;
+    double rh = reach / sin(arg);
+    if (rh > n / 2) rh = n / 2;
+    int r2 = (int)floor(rh * rh);
+    std::vector<std::pair<int, int>> cells;
+    int ri = (int)ceil(rh) + 1;
+    for (int Y = -ri; Y <= ri; ++Y)
+        for (int X = -ri; X <= ri; ++X) {
+            int x = X + n / 2, y = Y + n / 2;
+            if (x < 0 || y < 0 || x >= n || y >= n) continue;
+            if (X * X + Y * Y <= r2) cells.push_back(std::make_pair(X * X + Y * Y, (y << 16) | x));
+        }
+    if (cells.empty()) return 0;
+    std::sort(cells.begin(), cells.end());
+    std::vector<int> packed(cells.size());
+    for (size_t i = 0; i < cells.size(); ++i) packed[i] = cells[i].second;
+    TRON_CUDA(cudaMalloc(d_cells, packed.size() * sizeof(int)));
+    TRON_CUDA(cudaMemcpy(*d_cells, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice));
+    *nheavy = (int)packed.size(); *heavy_r2 = r2;
+    return 0;
 }
 
 static int pick_nbins(int npe)
@@ -179,12 +232,16 @@ struct CellGeom { int X, Y, Rlo, Rhi, kstart, count; };
 template <int CH, bool HALF>
 __device__ __forceinline__ void gather_cell(float2 (&acc)[CH], const GridLaunch &g,
                                             const float4 *__restrict__ tab, const int *__restrict__ tpe,
-                                            const void *samples, const CellGeom &c, int first, int step)
+                                            const char *samples, const CellGeom &c, int first, int step)
 {
     const float W = g.kb.W;
     const float Xf = (float)c.X, Yf = (float)c.Y, Rhif = (float)c.Rhi;
     const float xm = Xf - W, xp = Xf + W, ym = Yf - W, yp = Yf + W;
-    const int half_ro = g.nro / 2;
+    const bool same = g.nro == g.n;                       /* ridx = r (gridos 2) */
+    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
+    const size_t spoke_bytes = (size_t)g.nro * g.nc_total * esz;
+    const int samp_bytes = g.nc_total * (int)esz;
+    const char *centre = samples + (size_t)(g.nro / 2) * samp_bytes;
     for (int it = first; it < c.count; it += step) {
         int k = c.kstart + it;
         if (k >= g.npe) k -= g.npe;
@@ -194,6 +251,8 @@ __device__ __forceinline__ void gather_cell(float2 (&acc)[CH], const GridLaunch 
         float hi = fminf(fmaxf(ax, bx), fmaxf(ay, by)) + 1e-3f;
         lo = fmaxf(lo, -Rhif); hi = fminf(hi, Rhif);
         int r0 = (int)ceilf(lo), r1 = (int)floorf(hi);
+        if (r0 > r1) continue;
+        const char *spoke = centre + (size_t)__ldg(tpe + k) * spoke_bytes;   /* sample ro = nro/2 of this spoke */
         for (int r = r0; r <= r1; ++r) {
             if (abs(r) < c.Rlo) continue;                /* annulus, tron.cu:501-502,512,521 */
             float rf = (float)r;
@@ -203,56 +262,28 @@ __device__ __forceinline__ void gather_cell(float2 (&acc)[CH], const GridLaunch 
             if (!(fabsf(dy) < W)) continue;
             float w = kb_weight(dx, g.kb) * kb_weight(dy, g.kb);
             if (!(w > 0.f)) continue;
-            if (r == 0) w += w;                          /* both loops visit r = 0 */
-            int ridx = (r * g.nro) / g.n;                /* tron.cu:517 */
-            w *= fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);   /* tron.cu:412 */
-            int pe = __ldg(tpe + k);
-            size_t idx = ((size_t)pe * g.nro + (size_t)(ridx + half_ro)) * (size_t)g.nc_total;
-            fma_sample<CH, HALF>(acc, w, samples, idx);
+            int ridx = same ? r : (r * g.nro) / g.n;     /* tron.cu:517 */
+            float sdc = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);          /* tron.cu:412 */
+            w *= (r == 0) ? sdc + sdc : sdc;             /* both loops visit r = 0 */
+            fma_sample<CH, HALF>(acc, w, spoke + (ptrdiff_t)ridx * samp_bytes, 0);
         }
     }
 }
 
-template <int CH, bool HALF>
-__global__ void __launch_bounds__(256)
-grid_gather_kernel(const GridLaunch g)
+/* tron.cu:498-502 plus the window [kstart, kstart+count) of sorted spokes that can reach the cell */
+__device__ __forceinline__ void cell_setup(const GridLaunch &g, const int *__restrict__ lut, int x, int y, CellGeom &c)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = g.n;
-    const int tiles_x = (n + 15) >> 4;
-    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int x = tx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = ty * 16 + (warp >> 1) * 4 + (lane >> 3);
-    const int slice = blockIdx.y, chunk = blockIdx.z;
-    const bool valid = x < n && y < n;
-
-    const int tabi = g.tab_per_slice ? (g.z0 + slice) : 0;
-    const float4 *tab = g.tab_cs + (size_t)tabi * g.npe;
-    const int *tpe = g.tab_pe + (size_t)tabi * g.npe;
-    const int *lut = g.lut + (size_t)tabi * (g.nbins + 1);
-    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
-    const char *samples = (const char *)g.samples
-        + ((size_t)(g.z0 + slice) * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chunk * CH)) * esz;
-
-    float2 acc[CH];
-#pragma unroll
-    for (int i = 0; i < CH; ++i) acc[i] = make_float2(0.f, 0.f);
-
-    CellGeom c;
     c.X = x - n / 2; c.Y = y - n / 2;
     const float W = g.kb.W;
-    /* tron.cu:498-502 */
     float R = ref_hypotf((float)c.X, (float)c.Y);
     c.Rhi = (int)fminf(floorf(R + W), (float)(n / 2 - 1));
     c.Rlo = (int)fmaxf(ceilf(R - W), 0.f);
-    bool live = valid && c.Rlo <= c.Rhi;
-
-    /* angular window of spokes that can reach this cell */
+    /* a spoke reaches the cell only if its line passes within W*sqrt(2): |sin(angle diff)| < reach/R */
     const float reach = W * 1.41421368f + 2e-3f;
     float xr = reach / fmaxf(R, 1e-6f);
-    bool all_spokes = xr > 0.7f;
     c.kstart = 0; c.count = g.npe;
-    if (!all_spokes) {
+    if (xr <= 0.7f) {
         float T = atan2f((float)c.Y, (float)c.X);
         if (T < 0.f) T += PI_F;
         if (T >= PI_F) T -= PI_F;
@@ -269,36 +300,88 @@ grid_gather_kernel(const GridLaunch g)
             c.count = wrap ? (g.npe - ks) + ke : ke - ks;
         }
     }
-    if (!live) c.count = 0;
+    if (c.Rlo > c.Rhi) c.count = 0;
+}
 
-    /* heavy cells (near DC): the whole warp works on one cell at a time */
-    const int HEAVY = 96;
-    bool heavy = c.count >= HEAVY;
-    unsigned hmask = __ballot_sync(0xffffffffu, heavy);
-    if (!heavy) gather_cell<CH, HALF>(acc, g, tab, tpe, samples, c, 0, 1);
-    while (hmask) {
-        int src = __ffs(hmask) - 1;
-        hmask &= hmask - 1;
-        CellGeom h;
-        h.X = __shfl_sync(0xffffffffu, c.X, src); h.Y = __shfl_sync(0xffffffffu, c.Y, src);
-        h.Rlo = __shfl_sync(0xffffffffu, c.Rlo, src); h.Rhi = __shfl_sync(0xffffffffu, c.Rhi, src);
-        h.kstart = __shfl_sync(0xffffffffu, c.kstart, src); h.count = __shfl_sync(0xffffffffu, c.count, src);
-        float2 part[CH];
+/* main path: one thread per cell; cells inside the heavy disc are left to the heavy path */
+template <int CH, bool HALF>
+__device__ __forceinline__ void grid_tile_path(const GridLaunch &g, int block)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = g.n;
+    const int tiles_x = (n + 15) >> 4;
+    /* blocks are numbered heaviest tile first (tiles sorted by distance from DC, all
+     * slices of a rank before the next rank) so the long-running centre tiles start
+     * at once and the cheap outer tiles fill the tail */
+    const int rank = block / g.nslices, slice = block - rank * g.nslices;
+    const int tile = __ldg(g.tile_order + rank);
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int x = tx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = ty * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const int chunk = blockIdx.y;
+    if (x >= n || y >= n) return;
+
+    const int tabi = g.tab_per_slice ? (g.z0 + slice) : 0;
+    const float4 *tab = g.tab_cs + (size_t)tabi * g.npe;
+    const int *tpe = g.tab_pe + (size_t)tabi * g.npe;
+    const int *lut = g.lut + (size_t)tabi * (g.nbins + 1);
+    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
+    const char *samples = (const char *)g.samples
+        + ((size_t)(g.z0 + slice) * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chunk * CH)) * esz;
+
+    CellGeom c;
+    cell_setup(g, lut, x, y, c);
+    if (c.X * c.X + c.Y * c.Y <= g.heavy_r2) return;      /* integer test: identical on host and device */
+
+    float2 acc[CH];
 #pragma unroll
-        for (int i = 0; i < CH; ++i) part[i] = make_float2(0.f, 0.f);
-        gather_cell<CH, HALF>(part, g, tab, tpe, samples, h, lane, 32);
+    for (int i = 0; i < CH; ++i) acc[i] = make_float2(0.f, 0.f);
+    gather_cell<CH, HALF>(acc, g, tab, tpe, samples, c, 0, 1);
+
+    const size_t plane = (size_t)n * n;
+    float2 *out = g.grid + ((size_t)slice * g.nch + (size_t)chunk * CH) * plane + (size_t)y * n + x;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
+    for (int i = 0; i < CH; ++i)
+        out[(size_t)i * plane] = make_float2(acc[i].x * g.scale, acc[i].y * g.scale);
+}
+
+/* cells near DC see every spoke (hundreds of taps each): one warp per cell,
+ * lanes stride over the spokes, partial sums combined by shuffles */
+template <int CH, bool HALF>
+__device__ __forceinline__ void grid_heavy_path(const GridLaunch &g, int block)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = block / g.nslices, slice = block - grp * g.nslices;
+    const int ci = grp * 8 + warp;
+    const int chunk = blockIdx.y;
+    if (ci >= g.nheavy) return;
+    const int packed = __ldg(g.heavy_cells + ci);
+    const int x = packed & 0xffff, y = packed >> 16;
+    const int n = g.n;
+
+    const int tabi = g.tab_per_slice ? (g.z0 + slice) : 0;
+    const float4 *tab = g.tab_cs + (size_t)tabi * g.npe;
+    const int *tpe = g.tab_pe + (size_t)tabi * g.npe;
+    const int *lut = g.lut + (size_t)tabi * (g.nbins + 1);
+    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
+    const char *samples = (const char *)g.samples
+        + ((size_t)(g.z0 + slice) * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chunk * CH)) * esz;
+
+    CellGeom c;
+    cell_setup(g, lut, x, y, c);
+    float2 acc[CH];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                part[i].x += __shfl_xor_sync(0xffffffffu, part[i].x, o);
-                part[i].y += __shfl_xor_sync(0xffffffffu, part[i].y, o);
-            }
-            if (lane == src) acc[i] = part[i];
+    for (int i = 0; i < CH; ++i) acc[i] = make_float2(0.f, 0.f);
+    gather_cell<CH, HALF>(acc, g, tab, tpe, samples, c, lane, 32);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o);
+            acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
         }
     }
-
-    if (valid) {
+    if (lane == 0) {
         const size_t plane = (size_t)n * n;
         float2 *out = g.grid + ((size_t)slice * g.nch + (size_t)chunk * CH) * plane + (size_t)y * n + x;
 #pragma unroll
@@ -307,11 +390,21 @@ grid_gather_kernel(const GridLaunch g)
     }
 }
 
+/* one launch: the heavy-cell blocks come first (longest critical path), then the tiles */
+template <int CH, bool HALF>
+__global__ void __launch_bounds__(256)
+grid_gather_kernel(const GridLaunch g)
+{
+    const int heavy_blocks = ((g.nheavy + 7) >> 3) * g.nslices;
+    if ((int)blockIdx.x < heavy_blocks) grid_heavy_path<CH, HALF>(g, blockIdx.x);
+    else grid_tile_path<CH, HALF>(g, blockIdx.x - heavy_blocks);
+}
+
 template <int CH>
 static int launch_grid_ch(const GridLaunch &g, cudaStream_t s)
 {
     int tiles = ((g.n + 15) / 16) * ((g.n + 15) / 16);
-    dim3 grid(tiles, g.nslices, g.nch / CH);
+    dim3 grid((tiles + (g.nheavy + 7) / 8) * g.nslices, g.nch / CH);
     if (g.half_in) grid_gather_kernel<CH, true><<<grid, 256, 0, s>>>(g);
     else           grid_gather_kernel<CH, false><<<grid, 256, 0, s>>>(g);
     TRON_CUDA(cudaGetLastError());

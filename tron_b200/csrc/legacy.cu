@@ -100,7 +100,7 @@ gridradial2d(float2 *udata, const float2 *__restrict__ nudata, const int nxos, c
              const int skip_angles, const int flag_golden_angle)
 {
     (void)gridos;
-    const KbParams kb = make_kb(kernwidth);
+    const KbParams kb = make_kb_basic(kernwidth);
     const float W = kernwidth;
     const float scale = div_approx(rcp_approx((float)nxos), (float)npe);
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < nxos * nxos; id += blockDim.x * gridDim.x) {
@@ -144,7 +144,7 @@ degridradial2d(float2 *nudata, const float2 *__restrict__ udata, const int n, co
                const int skip_angles, const int flag_golden_angle)
 {
     (void)gridos;
-    const KbParams kb = make_kb(W);
+    const KbParams kb = make_kb_basic(W);
     const float c0 = (float)((n + 1) / 2);
     const float inv_nro = rcp_approx((float)nro);
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < nro * npe; id += blockDim.x * gridDim.x) {

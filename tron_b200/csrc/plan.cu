@@ -128,7 +128,7 @@ static void plan_release(tron_plan *p)
     if (!p) return;
     cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin);
     fft_plan_free(p->fft);
-    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd);
+    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->heavy_cells);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_in); cudaFree(p->d_out);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_in) cudaStreamDestroy(p->copy_in);
@@ -199,11 +199,16 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         PLAN_TRY(launch_build_tables(p->tabs, g.npe1work, 1, 0, cfg->skip_angles, cfg->golden_angle, 0, p->stream));
     }
     PLAN_TRY(fft_plan_init(p->fft, n, g.nx));
+    if (cfg->adjoint) {
+        PLAN_TRY(build_tile_order(&p->tile_order, n));
+        PLAN_TRY(build_heavy_cells(&p->heavy_cells, &p->nheavy, &p->heavy_r2, n, g.npe1work, cfg->kernwidth));
+    }
     PLAN_CUDA(cudaMalloc(&p->deapod_adj, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_CUDA(cudaMalloc(&p->deapod_fwd, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_TRY(launch_deapod_tables(p->deapod_adj, p->deapod_fwd, g.nx, n, cfg->kernwidth, cfg->gridos, p->stream));
 
     p->batch = cfg->adjoint ? pick_batch(p) : 1;
+    p->stage_timing = getenv("TRON_STAGE_TIMING") != nullptr;
     PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)p->batch * p->nch * n * n * sizeof(float2)));
     PLAN_CUDA(cudaMalloc(&p->d_tmp, (size_t)p->batch * p->nch * n * g.nx * sizeof(float2)));
     PLAN_CUDA(cudaStreamSynchronize(p->stream));
@@ -234,7 +239,8 @@ static GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, fl
     const tron_geometry &g = p->g;
     GridLaunch L;
     L.samples = d_samples; L.grid = d_grid;
-    L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.lut = p->tabs.lut;
+    L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.lut = p->tabs.lut; L.tile_order = p->tile_order;
+    L.heavy_cells = p->heavy_cells; L.nheavy = p->nheavy; L.heavy_r2 = p->heavy_r2;
     L.tab_per_slice = p->tabs.ntab > 1 ? 1 : 0;
     L.nbins = p->tabs.nbins;
     L.n = g.nxos; L.nro = g.nro; L.npe = g.npe1work;
@@ -261,8 +267,10 @@ static int run_adjoint_batch(tron_plan *p, void *d_out, const void *d_in, int z0
 {
     const tron_geometry &g = p->g;
     GridLaunch L = make_grid_launch(p, d_in, p->d_grid, z0, nb);
+    if (p->stage_timing) cudaEventRecord(p->ev_t[0], s);
     int rc = launch_grid(L, s);
     if (rc) return rc;
+    if (p->stage_timing) cudaEventRecord(p->ev_t[1], s);
     AdjFftLaunch a;
     a.grid = p->d_grid; a.tmp = p->d_tmp; a.deapod = p->deapod_adj;
     a.nslices = nb; a.nch = p->nch; a.nc_total = g.nc * g.nt; a.ch0 = g.coil_begin;
@@ -271,6 +279,14 @@ static int run_adjoint_batch(tron_plan *p, void *d_out, const void *d_in, int z0
     a.out = (char *)d_out + (size_t)z0 * per * p->out_elem_bytes;
     rc = launch_adj_fft(p->fft, a, s);
     p->last_launches += 3;
+    if (p->stage_timing && !rc) {               /* diagnostic mode: serialises host and device */
+        cudaEventRecord(p->ev_t[2], s);
+        cudaEventSynchronize(p->ev_t[2]);
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, p->ev_t[0], p->ev_t[1]);
+        cudaEventElapsedTime(&t1, p->ev_t[1], p->ev_t[2]);
+        p->last_ms[0] += t0; p->last_ms[1] += t1;
+    }
     return rc;
 }
 
@@ -298,6 +314,7 @@ extern "C" int tron_recon_device(tron_plan *p, void *d_out, const void *d_in, vo
     TRON_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     p->last_launches = 0;
+    p->last_ms[0] = p->last_ms[1] = p->last_ms[2] = 0.f;
     if (!p->cfg.adjoint) return run_forward(p, d_out, d_in, s);
     for (int z0 = 0; z0 < p->nslices; z0 += p->batch) {
         int nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;

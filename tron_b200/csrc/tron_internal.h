@@ -29,6 +29,8 @@ struct GridLaunch {               /* everything the gridding kernel needs */
     const void *samples;          /* first spoke of shard-local slice 0 */
     float2 *grid;                 /* [nslices][nch][n][n] */
     const float4 *tab_cs; const int *tab_pe; const int *lut;
+    const int *tile_order;        /* [tiles] heaviest (nearest DC) first */
+    const int *heavy_cells; int nheavy; int heavy_r2;   /* cells with X^2+Y^2 <= heavy_r2: one warp each */
     int tab_per_slice;            /* 1: table index = slice, 0: shared */
     int nbins;
     int n, nro, npe, nc_total, ch0, nch;
@@ -51,6 +53,8 @@ int launch_grid(const GridLaunch &g, cudaStream_t s);
 int launch_degrid(const DegridLaunch &d, cudaStream_t s);
 int launch_build_tables(SpokeTables &t, int npe, int nslices_tab, int slide, int skip, int golden,
                         int adjoint, cudaStream_t s);
+int build_tile_order(int **d_order, int n);
+int build_heavy_cells(int **d_cells, int *nheavy, int *heavy_r2, int n, int npe, float W);
 int launch_interleave(float2 *dst, const float2 *planar, int nch, int n, int nslices, cudaStream_t s);
 int launch_deinterleave(float2 *planar, const float2 *src, int nch, int n, cudaStream_t s);
 
@@ -60,7 +64,8 @@ struct FftPlan {
     int nkeep = 0;                /* nx */
     int nfac = 0; int fac[16];    /* radix schedule */
     float2 *tw = nullptr;         /* [n] exp(+2 pi i k / n) */
-    int lines = 0;                /* lines per CTA */
+    int lines = 0;                /* lines per CTA (generic path) */
+    int pow2 = 0;                 /* register radix-8 fast path available */
     size_t smem = 0;
 };
 int fft_plan_init(FftPlan &f, int n, int nkeep);
@@ -104,10 +109,13 @@ struct tron_plan {
     tronb::SpokeTables tabs;
     tronb::FftPlan fft;
     float *deapod_adj = nullptr, *deapod_fwd = nullptr;
+    int *tile_order = nullptr, *heavy_cells = nullptr;
+    int nheavy = 0, heavy_r2 = -1;
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
     void *d_in = nullptr, *d_out = nullptr;         /* device staging for the host API */
     size_t in_bytes = 0, out_bytes = 0;
     size_t in_elem_bytes = 8, out_elem_bytes = 8;
     int last_launches = 0;
+    int stage_timing = 0;                /* TRON_STAGE_TIMING: per-stage events (diagnostic) */
     float last_ms[3] = {0, 0, 0};
 };
