@@ -9,10 +9,12 @@
  * gather (registers accumulate, no atomics, no sample presort) but derives the
  * candidates analytically:
  *
- *   - per slice, the spokes are ordered by angle mod pi (a tiny plan-time table
- *     with an angular-bin LUT, built by spoke_table_kernel below);
+ *   - the spokes of a table are ordered by angle mod pi (plan-time table with an
+ *     angular-bin LUT, built by spoke_table_kernel below);
  *   - a cell at radius R only visits the spokes whose line passes within
- *     W*sqrt(2) of it: |angle - atan2(Y,X)| <= asin(W sqrt2 / R)  (mod pi);
+ *     W*sqrt(2) of it: |angle - atan2(Y,X)| <= asin(W sqrt2 / R)  (mod pi); the
+ *     bin range of that window is slice independent and comes from a per-cell
+ *     table (cell_table_kernel);
  *   - on each such spoke the candidate radii are the integer points of
  *     {r : |r ct - X| < W} n {r : |r st - Y| < W}, computed from 1/ct, 1/st
  *     with a conservative margin;
@@ -20,14 +22,22 @@
  *     evaluated with the reference's own operations (refmath.cuh): the set of
  *     taps is identical by construction, only the visiting order differs.
  *
+ * Sliding windows (-d): with golden angles the spoke angle depends on the
+ * ABSOLUTE spoke index (tron.cu:509,630), so the tap (cell, spoke, r) and its
+ * weight are the same in every slice whose window holds that spoke.  A thread
+ * therefore walks the union of the windows of GS consecutive slices once and
+ * feeds GS accumulator sets; the per-tap test/weight/load work is shared, only
+ * the FMAs (packed FFMA2) are per slice.
+ *
  * Reference quirks reproduced: support = square n annulus (Rlo..Rhi, SURVEY
  * F4); r = 0 counted twice when Rlo == 0 (F5); ridx = (r*nro)/nxos with C
- * truncation; golden angle from the ABSOLUTE spoke index in f32 (F16).
+ * truncation; golden angle from the absolute spoke index in f32 (F16).
  * Folded in: ramp density compensation a|ro - nro/2| + b (tron.cu:408-412) and
  * the 1/(nxos*npe) scale (tron.cu:532).
  *
- * Cells near DC see every spoke (hundreds of taps): those are processed by the
- * whole warp, lanes striding over spokes, partial sums combined by shuffles.
+ * Cells near DC see every spoke (hundreds of taps): one warp per cell, lanes
+ * striding over spokes, partial sums combined by shuffles; those blocks are
+ * numbered first, then the tiles nearest DC, so the longest work starts first.
  *
  * Output is planar: grid[slice][ch][row][col].
  */
@@ -40,6 +50,7 @@
 namespace tronb {
 
 #define PI_F 3.14159274101257324219f
+#define CELL_ALL_SPOKES 0x7fff
 
 __device__ __forceinline__ int angle_bin(float a, float lut_scale, int nbins)
 {
@@ -48,19 +59,25 @@ __device__ __forceinline__ int angle_bin(float a, float lut_scale, int nbins)
 }
 
 /* ---------------------------------------------------------------------- */
-/* plan-time spoke tables                                                  */
+/* plan-time tables                                                        */
 /* ---------------------------------------------------------------------- */
+
+/* One table per slice group (golden angle) or one shared table (linear).
+ * Entry k of a table: (cos, sin, 1/cos, 1/sin) of the k-th spoke by angle mod pi,
+ * pe_sorted[k] = index of that spoke relative to the group's first spoke, with
+ * bits 24.. = mask of the group's slices whose window [s*slide, s*slide+win) holds it. */
 __global__ void spoke_table_kernel(float4 *cs, int *pe_sorted, int *lut, float2 *cs_lin,
                                    float *key_unsorted, float *key_sorted,
-                                   int npe, int slide, int skip, int golden, int adjoint, int nbins)
+                                   int npe, int npe_formula, int tab_stride, int skip, int golden, int adjoint,
+                                   int nbins, int win, int slide, int gs, int nslices)
 {
     const int tab = blockIdx.x;
     float *ku = key_unsorted + (size_t)tab * npe;
     float *ks = key_sorted + (size_t)tab * npe;
     float2 *lin = cs_lin + (size_t)tab * npe;
     for (int pe = threadIdx.x; pe < npe; pe += blockDim.x) {
-        float t = adjoint ? ref_angle_grid(pe, npe, skip + tab * slide, golden)
-                          : ref_angle_degrid(pe, npe, skip, golden);
+        float t = adjoint ? ref_angle_grid(pe, npe_formula, skip + tab * tab_stride, golden)
+                          : ref_angle_degrid(pe, npe_formula, skip, golden);
         lin[pe] = make_float2(cos_approx(t), sin_approx(t));
         float key = fmodf(t, PI_F);
         if (key < 0.f) key += PI_F;
@@ -81,8 +98,11 @@ __global__ void spoke_table_kernel(float4 *cs, int *pe_sorted, int *lut, float2 
         float2 c = lin[pe];
         float ic = fabsf(c.x) > 1e-18f ? 1.0f / c.x : copysignf(1e18f, c.x);
         float is = fabsf(c.y) > 1e-18f ? 1.0f / c.y : copysignf(1e18f, c.y);
+        int mask = 0;
+        for (int s = 0; s < gs; ++s)
+            if (tab * gs + s < nslices && pe >= s * slide && pe < s * slide + win) mask |= 1 << s;
         csd[rank] = make_float4(c.x, c.y, ic, is);
-        ped[rank] = pe;
+        ped[rank] = pe | (mask << 24);
         ks[rank] = key;
     }
     __syncthreads();
@@ -95,6 +115,36 @@ __global__ void spoke_table_kernel(float4 *cs, int *pe_sorted, int *lut, float2 
             if (angle_bin(ks[mid], lut_scale, nbins) >= b) hi = mid; else lo = mid + 1;
         }
         l[b] = lo;
+    }
+}
+
+/* Per-cell, slice-independent geometry (tron.cu:498-502 and the angular window):
+ *   .x = Rlo | Rhi << 16          (Rlo > Rhi: no taps)
+ *   .y = (b0 & 0xffff) | b1 << 16 first/last angular bin (b0 may be negative, b1 may exceed nbins:
+ *        the window wraps), or CELL_ALL_SPOKES in the low half when every spoke must be visited. */
+__global__ void cell_table_kernel(int2 *cells, int n, float W, int nbins)
+{
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n * n; id += gridDim.x * blockDim.x) {
+        const int X = id % n - n / 2, Y = id / n - n / 2;
+        float R = ref_hypotf((float)X, (float)Y);
+        int Rhi = (int)fminf(floorf(R + W), (float)(n / 2 - 1));
+        int Rlo = (int)fmaxf(ceilf(R - W), 0.f);
+        if (Rlo > Rhi) { Rlo = 1; Rhi = 0; }
+        /* a spoke reaches the cell only if its line passes within W*sqrt(2): |sin(angle diff)| < reach/R */
+        const float reach = W * 1.41421368f + 2e-3f;
+        float xr = reach / fmaxf(R, 1e-6f);
+        int lo16 = CELL_ALL_SPOKES, b1 = 0;
+        if (xr <= 0.7f) {
+            float T = atan2f((float)Y, (float)X);
+            if (T < 0.f) T += PI_F;
+            if (T >= PI_F) T -= PI_F;
+            float delta = xr * fmaf(0.25f * xr, xr, 1.0f) + 2e-4f;     /* >= asin(xr) for xr <= 0.7 */
+            const float lut_scale = (float)nbins / PI_F;
+            int b0 = (int)floorf((T - delta) * lut_scale);
+            b1 = (int)floorf((T + delta) * lut_scale);
+            if (b1 - b0 + 1 < nbins) lo16 = b0 & 0xffff; else b1 = 0;
+        }
+        cells[id] = make_int2(Rlo | (Rhi << 16), lo16 | (b1 << 16));
     }
 }
 
@@ -154,10 +204,12 @@ static int pick_nbins(int npe)
     return nb;
 }
 
-int launch_build_tables(SpokeTables &t, int npe, int ntab, int slide, int skip, int golden,
-                        int adjoint, cudaStream_t s)
+/* npe: entries per table (union window of a slice group); npe_formula: the npe of the linear-angle
+ * formula (tron.cu:509,555); tab_stride: spokes between the first spokes of consecutive tables */
+int launch_build_tables(SpokeTables &t, int npe, int npe_formula, int ntab, int tab_stride, int skip, int golden,
+                        int adjoint, int win, int slide, int gs, int nslices, int n, float W, cudaStream_t s)
 {
-    t.ntab = ntab; t.nbins = pick_nbins(npe);
+    t.ntab = ntab; t.nbins = pick_nbins(npe); t.npe = npe; t.gs = gs;
     size_t ne = (size_t)ntab * npe;
     float *scratch = nullptr;
     TRON_CUDA(cudaMalloc(&t.cs_lin, ne * sizeof(float2)));
@@ -165,11 +217,16 @@ int launch_build_tables(SpokeTables &t, int npe, int ntab, int slide, int skip, 
         TRON_CUDA(cudaMalloc(&t.cs, ne * sizeof(float4)));
         TRON_CUDA(cudaMalloc(&t.pe, ne * sizeof(int)));
         TRON_CUDA(cudaMalloc(&t.lut, (size_t)ntab * (t.nbins + 1) * sizeof(int)));
+        TRON_CUDA(cudaMalloc(&t.cells, (size_t)n * n * sizeof(int2)));
+        int blocks = (n * n + 255) / 256; if (blocks > 4096) blocks = 4096;
+        cell_table_kernel<<<blocks, 256, 0, s>>>(t.cells, n, W, t.nbins);
+        TRON_CUDA(cudaGetLastError());
     }
     TRON_CUDA(cudaMalloc(&scratch, 2 * ne * sizeof(float)));
     int threads = npe >= 1024 ? 1024 : 256;
     spoke_table_kernel<<<ntab, threads, 0, s>>>(t.cs, t.pe, t.lut, t.cs_lin, scratch, scratch + ne,
-                                                npe, slide, skip, golden, adjoint, t.nbins);
+                                                npe, npe_formula, tab_stride, skip, golden, adjoint, t.nbins,
+                                                win, slide, gs, nslices);
     TRON_CUDA(cudaGetLastError());
     TRON_CUDA(cudaStreamSynchronize(s));
     TRON_CUDA(cudaFree(scratch));
@@ -179,48 +236,46 @@ int launch_build_tables(SpokeTables &t, int npe, int ntab, int slide, int skip, 
 /* ---------------------------------------------------------------------- */
 /* the gather                                                              */
 /* ---------------------------------------------------------------------- */
+
+/* acc.xy += w * v.xy as one packed FP32x2 FMA (FFMA2 on sm_100a) */
+__device__ __forceinline__ void ffma2(float2 &acc, float w, float2 v)
+{
+    unsigned long long a = *reinterpret_cast<unsigned long long *>(&acc);
+    float2 ww = make_float2(w, w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(a)
+        : "l"(*reinterpret_cast<unsigned long long *>(&ww)), "l"(*reinterpret_cast<unsigned long long *>(&v)));
+    acc = *reinterpret_cast<float2 *>(&a);
+}
+
+/* CH channels of one sample (contiguous, channel fastest); fp16 storage converts on load */
 template <int CH, bool HALF>
-__device__ __forceinline__ void fma_sample(float2 (&acc)[CH], float w, const void *base, size_t idx)
+__device__ __forceinline__ void load_sample(float2 (&v)[CH], const char *p)
 {
     if (!HALF) {
-        const float2 *p = (const float2 *)base + idx;
         if (CH % 2 == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 2; ++i) {
-                float4 v = __ldg((const float4 *)p + i);
-                acc[2 * i].x = fmaf(w, v.x, acc[2 * i].x);
-                acc[2 * i].y = fmaf(w, v.y, acc[2 * i].y);
-                acc[2 * i + 1].x = fmaf(w, v.z, acc[2 * i + 1].x);
-                acc[2 * i + 1].y = fmaf(w, v.w, acc[2 * i + 1].y);
+                float4 q = __ldg((const float4 *)p + i);
+                v[2 * i] = make_float2(q.x, q.y); v[2 * i + 1] = make_float2(q.z, q.w);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < CH; ++i) {
-                float2 v = __ldg(p + i);
-                acc[i].x = fmaf(w, v.x, acc[i].x);
-                acc[i].y = fmaf(w, v.y, acc[i].y);
-            }
+            for (int i = 0; i < CH; ++i) v[i] = __ldg((const float2 *)p + i);
         }
-    } else {                                   /* fp16 storage: native half2 load + convert */
-        const __half2 *p = (const __half2 *)base + idx;
+    } else {
         if (CH % 2 == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 2; ++i) {
                 uint2 raw = __ldg((const uint2 *)p + i);
-                float2 a = __half22float2(*reinterpret_cast<__half2 *>(&raw.x));
-                float2 b = __half22float2(*reinterpret_cast<__half2 *>(&raw.y));
-                acc[2 * i].x = fmaf(w, a.x, acc[2 * i].x);
-                acc[2 * i].y = fmaf(w, a.y, acc[2 * i].y);
-                acc[2 * i + 1].x = fmaf(w, b.x, acc[2 * i + 1].x);
-                acc[2 * i + 1].y = fmaf(w, b.y, acc[2 * i + 1].y);
+                v[2 * i] = __half22float2(*reinterpret_cast<__half2 *>(&raw.x));
+                v[2 * i + 1] = __half22float2(*reinterpret_cast<__half2 *>(&raw.y));
             }
         } else {
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
                 unsigned raw = __ldg((const unsigned *)p + i);
-                float2 a = __half22float2(*reinterpret_cast<__half2 *>(&raw));
-                acc[i].x = fmaf(w, a.x, acc[i].x);
-                acc[i].y = fmaf(w, a.y, acc[i].y);
+                v[i] = __half22float2(*reinterpret_cast<__half2 *>(&raw));
             }
         }
     }
@@ -228,9 +283,30 @@ __device__ __forceinline__ void fma_sample(float2 (&acc)[CH], float w, const voi
 
 struct CellGeom { int X, Y, Rlo, Rhi, kstart, count; };
 
+/* window [kstart, kstart+count) of sorted spokes that can reach the cell (circular in the table) */
+__device__ __forceinline__ void cell_setup(const GridLaunch &g, const int *__restrict__ lut, int x, int y, CellGeom &c)
+{
+    const int n = g.n;
+    c.X = x - n / 2; c.Y = y - n / 2;
+    const int2 t = __ldg(g.cells + (size_t)y * n + x);
+    c.Rlo = t.x & 0xffff; c.Rhi = t.x >> 16;
+    c.kstart = 0; c.count = g.npe;
+    const int lo16 = t.y & 0xffff;
+    if (lo16 != CELL_ALL_SPOKES) {
+        int b0 = (int)(short)lo16, b1 = t.y >> 16;
+        bool wrap = false;
+        if (b0 < 0) { b0 += g.nbins; wrap = true; }
+        if (b1 >= g.nbins) { b1 -= g.nbins; wrap = true; }
+        int ks = __ldg(lut + b0), ke = __ldg(lut + b1 + 1);
+        c.kstart = ks;
+        c.count = wrap ? (g.npe - ks) + ke : ke - ks;
+    }
+    if (c.Rlo > c.Rhi) c.count = 0;
+}
+
 /* Visit sorted-table entries kstart + first, kstart + first + step, ... (< count, circular). */
-template <int CH, bool HALF>
-__device__ __forceinline__ void gather_cell(float2 (&acc)[CH], const GridLaunch &g,
+template <int CH, int GS, bool HALF>
+__device__ __forceinline__ void gather_cell(float2 (&acc)[GS][CH], const GridLaunch &g,
                                             const float4 *__restrict__ tab, const int *__restrict__ tpe,
                                             const char *samples, const CellGeom &c, int first, int step)
 {
@@ -252,7 +328,10 @@ __device__ __forceinline__ void gather_cell(float2 (&acc)[CH], const GridLaunch 
         lo = fmaxf(lo, -Rhif); hi = fminf(hi, Rhif);
         int r0 = (int)ceilf(lo), r1 = (int)floorf(hi);
         if (r0 > r1) continue;
-        const char *spoke = centre + (size_t)__ldg(tpe + k) * spoke_bytes;   /* sample ro = nro/2 of this spoke */
+        const int pm = __ldg(tpe + k);
+        const int mask = GS > 1 ? (pm >> 24) : 1;
+        if (GS > 1 && mask == 0) continue;               /* spoke outside every window of a partial group */
+        const char *spoke = centre + (size_t)(pm & 0xffffff) * spoke_bytes;  /* sample ro = nro/2 of this spoke */
         for (int r = r0; r <= r1; ++r) {
             if (abs(r) < c.Rlo) continue;                /* annulus, tron.cu:501-502,512,521 */
             float rf = (float)r;
@@ -265,55 +344,58 @@ __device__ __forceinline__ void gather_cell(float2 (&acc)[CH], const GridLaunch 
             int ridx = same ? r : (r * g.nro) / g.n;     /* tron.cu:517 */
             float sdc = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);          /* tron.cu:412 */
             w *= (r == 0) ? sdc + sdc : sdc;             /* both loops visit r = 0 */
-            fma_sample<CH, HALF>(acc, w, spoke + (ptrdiff_t)ridx * samp_bytes, 0);
+            float2 v[CH];
+            load_sample<CH, HALF>(v, spoke + (ptrdiff_t)ridx * samp_bytes);
+#pragma unroll
+            for (int s = 0; s < GS; ++s) {
+                if (GS == 1 || (mask >> s) & 1) {
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) ffma2(acc[s][i], w, v[i]);
+                }
+            }
         }
     }
 }
 
-/* tron.cu:498-502 plus the window [kstart, kstart+count) of sorted spokes that can reach the cell */
-__device__ __forceinline__ void cell_setup(const GridLaunch &g, const int *__restrict__ lut, int x, int y, CellGeom &c)
+template <int CH, int GS, bool HALF>
+__device__ __forceinline__ void group_pointers(const GridLaunch &g, int grp, int chunk, const float4 *&tab,
+                                               const int *&tpe, const int *&lut, const char *&samples)
 {
-    const int n = g.n;
-    c.X = x - n / 2; c.Y = y - n / 2;
-    const float W = g.kb.W;
-    float R = ref_hypotf((float)c.X, (float)c.Y);
-    c.Rhi = (int)fminf(floorf(R + W), (float)(n / 2 - 1));
-    c.Rlo = (int)fmaxf(ceilf(R - W), 0.f);
-    /* a spoke reaches the cell only if its line passes within W*sqrt(2): |sin(angle diff)| < reach/R */
-    const float reach = W * 1.41421368f + 2e-3f;
-    float xr = reach / fmaxf(R, 1e-6f);
-    c.kstart = 0; c.count = g.npe;
-    if (xr <= 0.7f) {
-        float T = atan2f((float)c.Y, (float)c.X);
-        if (T < 0.f) T += PI_F;
-        if (T >= PI_F) T -= PI_F;
-        float delta = xr * fmaf(0.25f * xr, xr, 1.0f) + 2e-4f;     /* >= asin(xr) for xr <= 0.7 */
-        const float lut_scale = (float)g.nbins / PI_F;
-        int b0 = (int)floorf((T - delta) * lut_scale);
-        int b1 = (int)floorf((T + delta) * lut_scale);
-        if (b1 - b0 + 1 < g.nbins) {
-            bool wrap = false;
-            if (b0 < 0) { b0 += g.nbins; wrap = true; }
-            if (b1 >= g.nbins) { b1 -= g.nbins; wrap = true; }
-            int ks = __ldg(lut + b0), ke = __ldg(lut + b1 + 1);
-            c.kstart = ks;
-            c.count = wrap ? (g.npe - ks) + ke : ke - ks;
-        }
+    const int ug = g.z0 / GS + grp;                       /* slice group, shard-local */
+    const int tabi = g.tab_per_slice ? ug : 0;
+    tab = g.tab_cs + (size_t)tabi * g.npe;
+    tpe = g.tab_pe + (size_t)tabi * g.npe;
+    lut = g.lut + (size_t)tabi * (g.nbins + 1);
+    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
+    samples = (const char *)g.samples
+        + ((size_t)ug * GS * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chunk * CH)) * esz;
+}
+
+template <int CH, int GS>
+__device__ __forceinline__ void store_cell(const GridLaunch &g, const float2 (&acc)[GS][CH], int grp, int chunk,
+                                           int x, int y)
+{
+    const size_t plane = (size_t)g.n * g.n;
+    const int zg = (g.z0 / GS + grp) * GS;
+#pragma unroll
+    for (int s = 0; s < GS; ++s) {
+        const int zl = zg + s - g.z0;                      /* slice index inside this launch */
+        if (zl < 0 || zl >= g.nslices) continue;
+        float2 *out = g.grid + ((size_t)zl * g.nch + (size_t)chunk * CH) * plane + (size_t)y * g.n + x;
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+            out[(size_t)i * plane] = make_float2(acc[s][i].x * g.scale, acc[s][i].y * g.scale);
     }
-    if (c.Rlo > c.Rhi) c.count = 0;
 }
 
 /* main path: one thread per cell; cells inside the heavy disc are left to the heavy path */
-template <int CH, bool HALF>
+template <int CH, int GS, bool HALF>
 __device__ __forceinline__ void grid_tile_path(const GridLaunch &g, int block)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = g.n;
     const int tiles_x = (n + 15) >> 4;
-    /* blocks are numbered heaviest tile first (tiles sorted by distance from DC, all
-     * slices of a rank before the next rank) so the long-running centre tiles start
-     * at once and the cheap outer tiles fill the tail */
-    const int rank = block / g.nslices, slice = block - rank * g.nslices;
+    const int rank = block / g.ngroups, grp = block - rank * g.ngroups;
     const int tile = __ldg(g.tile_order + rank);
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int x = tx * 16 + (warp & 1) * 8 + (lane & 7);
@@ -321,92 +403,74 @@ __device__ __forceinline__ void grid_tile_path(const GridLaunch &g, int block)
     const int chunk = blockIdx.y;
     if (x >= n || y >= n) return;
 
-    const int tabi = g.tab_per_slice ? (g.z0 + slice) : 0;
-    const float4 *tab = g.tab_cs + (size_t)tabi * g.npe;
-    const int *tpe = g.tab_pe + (size_t)tabi * g.npe;
-    const int *lut = g.lut + (size_t)tabi * (g.nbins + 1);
-    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
-    const char *samples = (const char *)g.samples
-        + ((size_t)(g.z0 + slice) * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chunk * CH)) * esz;
-
+    const float4 *tab; const int *tpe, *lut; const char *samples;
+    group_pointers<CH, GS, HALF>(g, grp, chunk, tab, tpe, lut, samples);
     CellGeom c;
     cell_setup(g, lut, x, y, c);
     if (c.X * c.X + c.Y * c.Y <= g.heavy_r2) return;      /* integer test: identical on host and device */
 
-    float2 acc[CH];
+    float2 acc[GS][CH];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) acc[i] = make_float2(0.f, 0.f);
-    gather_cell<CH, HALF>(acc, g, tab, tpe, samples, c, 0, 1);
-
-    const size_t plane = (size_t)n * n;
-    float2 *out = g.grid + ((size_t)slice * g.nch + (size_t)chunk * CH) * plane + (size_t)y * n + x;
+    for (int s = 0; s < GS; ++s)
 #pragma unroll
-    for (int i = 0; i < CH; ++i)
-        out[(size_t)i * plane] = make_float2(acc[i].x * g.scale, acc[i].y * g.scale);
+        for (int i = 0; i < CH; ++i) acc[s][i] = make_float2(0.f, 0.f);
+    gather_cell<CH, GS, HALF>(acc, g, tab, tpe, samples, c, 0, 1);
+    store_cell<CH, GS>(g, acc, grp, chunk, x, y);
 }
 
-/* cells near DC see every spoke (hundreds of taps each): one warp per cell,
- * lanes stride over the spokes, partial sums combined by shuffles */
-template <int CH, bool HALF>
+/* heavy path: one warp per cell, lanes stride over the spokes, shuffle reduction */
+template <int CH, int GS, bool HALF>
 __device__ __forceinline__ void grid_heavy_path(const GridLaunch &g, int block)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grp = block / g.nslices, slice = block - grp * g.nslices;
-    const int ci = grp * 8 + warp;
+    const int hg = block / g.ngroups, grp = block - hg * g.ngroups;
+    const int ci = hg * 8 + warp;
     const int chunk = blockIdx.y;
     if (ci >= g.nheavy) return;
     const int packed = __ldg(g.heavy_cells + ci);
     const int x = packed & 0xffff, y = packed >> 16;
-    const int n = g.n;
 
-    const int tabi = g.tab_per_slice ? (g.z0 + slice) : 0;
-    const float4 *tab = g.tab_cs + (size_t)tabi * g.npe;
-    const int *tpe = g.tab_pe + (size_t)tabi * g.npe;
-    const int *lut = g.lut + (size_t)tabi * (g.nbins + 1);
-    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
-    const char *samples = (const char *)g.samples
-        + ((size_t)(g.z0 + slice) * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chunk * CH)) * esz;
-
+    const float4 *tab; const int *tpe, *lut; const char *samples;
+    group_pointers<CH, GS, HALF>(g, grp, chunk, tab, tpe, lut, samples);
     CellGeom c;
     cell_setup(g, lut, x, y, c);
-    float2 acc[CH];
+    float2 acc[GS][CH];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) acc[i] = make_float2(0.f, 0.f);
-    gather_cell<CH, HALF>(acc, g, tab, tpe, samples, c, lane, 32);
+    for (int s = 0; s < GS; ++s)
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
+        for (int i = 0; i < CH; ++i) acc[s][i] = make_float2(0.f, 0.f);
+    gather_cell<CH, GS, HALF>(acc, g, tab, tpe, samples, c, lane, 32);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o);
-            acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc[s][i].x += __shfl_xor_sync(0xffffffffu, acc[s][i].x, o);
+                acc[s][i].y += __shfl_xor_sync(0xffffffffu, acc[s][i].y, o);
+            }
         }
-    }
-    if (lane == 0) {
-        const size_t plane = (size_t)n * n;
-        float2 *out = g.grid + ((size_t)slice * g.nch + (size_t)chunk * CH) * plane + (size_t)y * n + x;
-#pragma unroll
-        for (int i = 0; i < CH; ++i)
-            out[(size_t)i * plane] = make_float2(acc[i].x * g.scale, acc[i].y * g.scale);
-    }
+    if (lane == 0) store_cell<CH, GS>(g, acc, grp, chunk, x, y);
 }
 
 /* one launch: the heavy-cell blocks come first (longest critical path), then the tiles */
-template <int CH, bool HALF>
+template <int CH, int GS, bool HALF>
 __global__ void __launch_bounds__(256)
 grid_gather_kernel(const GridLaunch g)
 {
-    const int heavy_blocks = ((g.nheavy + 7) >> 3) * g.nslices;
-    if ((int)blockIdx.x < heavy_blocks) grid_heavy_path<CH, HALF>(g, blockIdx.x);
-    else grid_tile_path<CH, HALF>(g, blockIdx.x - heavy_blocks);
+    const int heavy_blocks = ((g.nheavy + 7) >> 3) * g.ngroups;
+    if ((int)blockIdx.x < heavy_blocks) grid_heavy_path<CH, GS, HALF>(g, blockIdx.x);
+    else grid_tile_path<CH, GS, HALF>(g, blockIdx.x - heavy_blocks);
 }
 
-template <int CH>
-static int launch_grid_ch(const GridLaunch &g, cudaStream_t s)
+template <int CH, int GS>
+static int launch_grid_cg(GridLaunch g, cudaStream_t s)
 {
     int tiles = ((g.n + 15) / 16) * ((g.n + 15) / 16);
-    dim3 grid((tiles + (g.nheavy + 7) / 8) * g.nslices, g.nch / CH);
-    if (g.half_in) grid_gather_kernel<CH, true><<<grid, 256, 0, s>>>(g);
-    else           grid_gather_kernel<CH, false><<<grid, 256, 0, s>>>(g);
+    g.ngroups = (g.z0 + g.nslices - 1) / GS - g.z0 / GS + 1;
+    dim3 grid((tiles + (g.nheavy + 7) / 8) * g.ngroups, g.nch / CH);
+    if (g.half_in) grid_gather_kernel<CH, GS, true><<<grid, 256, 0, s>>>(g);
+    else           grid_gather_kernel<CH, GS, false><<<grid, 256, 0, s>>>(g);
     TRON_CUDA(cudaGetLastError());
     return 0;
 }
@@ -417,11 +481,18 @@ int launch_grid(const GridLaunch &g, cudaStream_t s)
     size_t esz = g.half_in ? 4 : 8;
     bool aligned = (((uintptr_t)g.samples) % (2 * esz) == 0) && (g.nc_total % 2 == 0) && (g.ch0 % 2 == 0);
     if (g.nslices <= 0 || g.nch <= 0) return 0;
-    if (!aligned || g.nch % 2) return launch_grid_ch<1>(g, s);
-    if (g.nch % 8 == 0) return launch_grid_ch<8>(g, s);
-    if (g.nch % 6 == 0) return launch_grid_ch<6>(g, s);
-    if (g.nch % 4 == 0) return launch_grid_ch<4>(g, s);
-    return launch_grid_ch<2>(g, s);
+    if (g.gs == 4) {                                      /* sliding windows share taps across 4 slices */
+        if (!aligned || g.nch % 2) return launch_grid_cg<1, 4>(g, s);
+        if (g.nch % 6 == 0) return launch_grid_cg<6, 4>(g, s);
+        if (g.nch % 4 == 0) return launch_grid_cg<4, 4>(g, s);
+        return launch_grid_cg<2, 4>(g, s);
+    }
+    if (g.gs != 1) { set_error("unsupported slice group size %d", g.gs); return TRON_EINVAL; }
+    if (!aligned || g.nch % 2) return launch_grid_cg<1, 1>(g, s);
+    if (g.nch % 8 == 0) return launch_grid_cg<8, 1>(g, s);
+    if (g.nch % 6 == 0) return launch_grid_cg<6, 1>(g, s);
+    if (g.nch % 4 == 0) return launch_grid_cg<4, 1>(g, s);
+    return launch_grid_cg<2, 1>(g, s);
 }
 
 /* ---------------------------------------------------------------------- */

@@ -126,7 +126,7 @@ extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
 static void plan_release(tron_plan *p)
 {
     if (!p) return;
-    cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin);
+    cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
     fft_plan_free(p->fft);
     cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->heavy_cells);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_in); cudaFree(p->d_out);
@@ -192,22 +192,33 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
 
     const int n = g.nxos;
     if (cfg->adjoint) {
-        int ntab = cfg->golden_angle ? p->nslices : 1;
+        /* golden angles + overlapping windows: 4 consecutive slices share their taps (grid.cu) */
+        int gs = 1;
+        if (cfg->golden_angle && p->nslices > 1 && 2 * g.prof_slide <= g.npe1work) gs = 4;
+        const char *eg = getenv("TRON_GROUP");
+        if (eg && cfg->golden_angle && (atoi(eg) == 1 || atoi(eg) == 4)) gs = atoi(eg);
+        int nun = (gs - 1) * g.prof_slide + g.npe1work;                 /* union window of a group */
+        int ntab = cfg->golden_angle ? (p->nslices + gs - 1) / gs : 1;
         int skip = cfg->skip_angles + (cfg->golden_angle ? g.slice_begin * g.prof_slide : 0);
-        PLAN_TRY(launch_build_tables(p->tabs, g.npe1work, ntab, g.prof_slide, skip, cfg->golden_angle, 1, p->stream));
+        PLAN_TRY(launch_build_tables(p->tabs, nun, g.npe1work, ntab, gs * g.prof_slide, skip, cfg->golden_angle, 1,
+                                     g.npe1work, g.prof_slide, gs, p->nslices, n, cfg->kernwidth, p->stream));
     } else {
-        PLAN_TRY(launch_build_tables(p->tabs, g.npe1work, 1, 0, cfg->skip_angles, cfg->golden_angle, 0, p->stream));
+        PLAN_TRY(launch_build_tables(p->tabs, g.npe1work, g.npe1work, 1, 0, cfg->skip_angles, cfg->golden_angle, 0,
+                                     g.npe1work, 0, 1, 1, n, cfg->kernwidth, p->stream));
     }
     PLAN_TRY(fft_plan_init(p->fft, n, g.nx));
     if (cfg->adjoint) {
         PLAN_TRY(build_tile_order(&p->tile_order, n));
-        PLAN_TRY(build_heavy_cells(&p->heavy_cells, &p->nheavy, &p->heavy_r2, n, g.npe1work, cfg->kernwidth));
+        PLAN_TRY(build_heavy_cells(&p->heavy_cells, &p->nheavy, &p->heavy_r2, n, p->tabs.npe, cfg->kernwidth));
     }
     PLAN_CUDA(cudaMalloc(&p->deapod_adj, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_CUDA(cudaMalloc(&p->deapod_fwd, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_TRY(launch_deapod_tables(p->deapod_adj, p->deapod_fwd, g.nx, n, cfg->kernwidth, cfg->gridos, p->stream));
 
     p->batch = cfg->adjoint ? pick_batch(p) : 1;
+    if (cfg->adjoint && p->tabs.gs > 1) {                /* launches start on group boundaries */
+        p->batch = ((p->batch + p->tabs.gs - 1) / p->tabs.gs) * p->tabs.gs;
+    }
     p->stage_timing = getenv("TRON_STAGE_TIMING") != nullptr;
     PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)p->batch * p->nch * n * n * sizeof(float2)));
     PLAN_CUDA(cudaMalloc(&p->d_tmp, (size_t)p->batch * p->nch * n * g.nx * sizeof(float2)));
@@ -239,11 +250,12 @@ static GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, fl
     const tron_geometry &g = p->g;
     GridLaunch L;
     L.samples = d_samples; L.grid = d_grid;
-    L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.lut = p->tabs.lut; L.tile_order = p->tile_order;
+    L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.lut = p->tabs.lut; L.cells = p->tabs.cells;
+    L.tile_order = p->tile_order;
     L.heavy_cells = p->heavy_cells; L.nheavy = p->nheavy; L.heavy_r2 = p->heavy_r2;
     L.tab_per_slice = p->tabs.ntab > 1 ? 1 : 0;
     L.nbins = p->tabs.nbins;
-    L.n = g.nxos; L.nro = g.nro; L.npe = g.npe1work;
+    L.n = g.nxos; L.nro = g.nro; L.npe = p->tabs.npe; L.gs = p->tabs.gs; L.ngroups = 0;
     L.nc_total = g.nc * g.nt; L.ch0 = g.coil_begin; L.nch = p->nch;
     L.z0 = z0; L.nslices = nb; L.slide = g.prof_slide;
     L.kb = make_kb(p->cfg.kernwidth);

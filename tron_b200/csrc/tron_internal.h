@@ -16,24 +16,29 @@ int  cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 #define TRON_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
     return tronb::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
 
-/* One sorted-spoke table per slice (golden angle) or one shared table (linear). */
+/* One sorted-spoke table per slice group (golden angle) or one shared table (linear). */
 struct SpokeTables {
     float4 *cs = nullptr;     /* [ntab][npe]  (cos, sin, 1/cos, 1/sin), sorted by angle mod pi */
-    int    *pe = nullptr;     /* [ntab][npe]  window-relative spoke index of each sorted entry */
+    int    *pe = nullptr;     /* [ntab][npe]  group-relative spoke index | slice mask << 24 */
     int    *lut = nullptr;    /* [ntab][nbins+1] first sorted entry of each angular bin */
     float2 *cs_lin = nullptr; /* [ntab][npe]  (cos, sin) in acquisition order (degridding) */
+    int2   *cells = nullptr;  /* [n][n] slice-independent cell geometry (band, angular bins) */
     int ntab = 0, nbins = 0;
+    int npe = 0;              /* entries per table = union window of a slice group */
+    int gs = 1;               /* slices per group */
 };
 
 struct GridLaunch {               /* everything the gridding kernel needs */
     const void *samples;          /* first spoke of shard-local slice 0 */
     float2 *grid;                 /* [nslices][nch][n][n] */
-    const float4 *tab_cs; const int *tab_pe; const int *lut;
+    const float4 *tab_cs; const int *tab_pe; const int *lut; const int2 *cells;
     const int *tile_order;        /* [tiles] heaviest (nearest DC) first */
     const int *heavy_cells; int nheavy; int heavy_r2;   /* cells with X^2+Y^2 <= heavy_r2: one warp each */
-    int tab_per_slice;            /* 1: table index = slice, 0: shared */
+    int tab_per_slice;            /* 1: table index = slice group, 0: shared */
     int nbins;
-    int n, nro, npe, nc_total, ch0, nch;
+    int n, nro, nc_total, ch0, nch;
+    int npe;                      /* entries per spoke table (union window of a group) */
+    int gs, ngroups;              /* slices per group; groups touched by this launch */
     int z0, nslices, slide;
     KbParams kb;
     float sdc_a, sdc_b, scale;
@@ -51,8 +56,8 @@ struct DegridLaunch {
 
 int launch_grid(const GridLaunch &g, cudaStream_t s);
 int launch_degrid(const DegridLaunch &d, cudaStream_t s);
-int launch_build_tables(SpokeTables &t, int npe, int nslices_tab, int slide, int skip, int golden,
-                        int adjoint, cudaStream_t s);
+int launch_build_tables(SpokeTables &t, int npe, int npe_formula, int ntab, int tab_stride, int skip, int golden,
+                        int adjoint, int win, int slide, int gs, int nslices, int n, float W, cudaStream_t s);
 int build_tile_order(int **d_order, int n);
 int build_heavy_cells(int **d_cells, int *nheavy, int *heavy_r2, int n, int npe, float W);
 int launch_interleave(float2 *dst, const float2 *planar, int nch, int n, int nslices, cudaStream_t s);
