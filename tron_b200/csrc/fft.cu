@@ -40,8 +40,21 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+/* complex add/sub as one packed FP32x2 instruction (FADD2 on sm_100a) */
+__device__ __forceinline__ float2 cadd(float2 a, float2 b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b)
+{
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
 /* multiply by s*i, s = +-1 */
 __device__ __forceinline__ float2 cmuli(float2 a, float s) { return make_float2(-s * a.y, s * a.x); }
 
@@ -352,6 +365,26 @@ template <int N, int L> struct P2 {
     static constexpr int PITCH = BASE + ((WANT - BASE % 16) + 16) % 16 + (((WANT - BASE % 16) + 16) % 16 == 0 ? 16 : 0);
 };
 
+/* phys(base + off) - phys(base) for the offsets the stages use: compile-time constants because the
+ * low four bits of the base are known (see the access patterns in p2_stage / p2_stages) */
+template <int Ns> __device__ __forceinline__ constexpr int p2_woff(int t)
+{
+    return Ns % 16 == 0 ? t * (Ns + Ns / 16) : (Ns == 8 ? 8 * t + (t >> 1) : t);
+}
+template <int T> __device__ __forceinline__ constexpr int p2_roff(int q)
+{
+    return T % 16 == 0 ? q * (T + T / 16) : q * T + ((q * T) >> 4);       /* T = 8: j < 8, so no carry */
+}
+
+/* the threads of one line synchronise among themselves (named barrier), not with the whole CTA */
+template <int N>
+__device__ __forceinline__ void p2_line_sync(int l)
+{
+    constexpr int T = N / 8;
+    if (T >= 32) asm volatile("bar.sync %0, %1;" ::"r"(l + 1), "n"(T) : "memory");
+    else __syncthreads();
+}
+
 template <int N, int Ns, int R, int SGN>
 __device__ __forceinline__ void p2_stage(float2 (&v)[8], float2 *dst, const float2 *stw, int j)
 {
@@ -380,24 +413,27 @@ __device__ __forceinline__ void p2_stage(float2 (&v)[8], float2 *dst, const floa
             }
         }
         Dft<R>::run(x, (float)SGN);
-        const int j0 = (b - k) * R + k;
+        float2 *d = dst + phys((b - k) * R + k);
 #pragma unroll
-        for (int t = 0; t < R; ++t) dst[phys(j0 + t * Ns)] = x[t];
+        for (int t = 0; t < R; ++t) d[p2_woff<Ns>(t)] = x[t];
     }
 }
 
 template <int N, int Ns, int SGN>
-__device__ __forceinline__ void p2_stages(float2 (&v)[8], float2 *bufA, float2 *bufB, const float2 *stw, int j)
+__device__ __forceinline__ void p2_stages(float2 (&v)[8], float2 *bufA, float2 *bufB, const float2 *stw, int j, int l)
 {
     constexpr int REM = N / Ns;
     constexpr int R = REM >= 8 ? 8 : REM;
     p2_stage<N, Ns, R, SGN>(v, bufA, stw, j);
-    __syncthreads();
     if constexpr (Ns * R < N) {
         constexpr int T = N / 8;
+        p2_line_sync<N>(l);
+        const float2 *s = bufA + phys(j);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = bufA[phys(j + q * T)];
-        p2_stages<N, Ns * R, SGN>(v, bufB, bufA, stw, j);
+        for (int q = 0; q < 8; ++q) v[q] = s[p2_roff<T>(q)];
+        p2_stages<N, Ns * R, SGN>(v, bufB, bufA, stw, j, l);
+    } else {
+        __syncthreads();                     /* the store phase reads every line of the CTA */
     }
 }
 
@@ -407,9 +443,9 @@ template <int N> __host__ __device__ constexpr int p2_nstages() { int s = 0, m =
 /* Transform: registers in (element j + q*T of the line), result in shared memory, natural order.
  * Returns the line base inside the result buffer.  lineA/lineB are this line's two buffers. */
 template <int N, int SGN>
-__device__ __forceinline__ float2 *p2_fft(float2 (&v)[8], float2 *lineA, float2 *lineB, const float2 *stw, int j)
+__device__ __forceinline__ float2 *p2_fft(float2 (&v)[8], float2 *lineA, float2 *lineB, const float2 *stw, int j, int l)
 {
-    p2_stages<N, 1, SGN>(v, lineA, lineB, stw, j);
+    p2_stages<N, 1, SGN>(v, lineA, lineB, stw, j, l);
     return (p2_nstages<N>() & 1) ? lineA : lineB;
 }
 
@@ -429,7 +465,7 @@ p2_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const f
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = g[j + q * T];
     __syncthreads();
-    float2 *res = p2_fft<N, +1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j) - l * PITCH;
+    float2 *res = p2_fft<N, +1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j, l) - l * PITCH;
     const int w = (N - nkeep) / 2, h = N / 2;
     float2 *out = tmp + plane * (size_t)nkeep * N + y0;
     for (int idx = threadIdx.x; idx < nkeep * L; idx += L * T) {
@@ -472,7 +508,7 @@ p2_adj_pass_b(const float2 *__restrict__ tmp, void *__restrict__ outv, const flo
             for (int q = 0; q < 8; ++q) nv[q] = line_ok ? src[(size_t)(ch + 1) * chan_stride + q * T] : make_float2(0.f, 0.f);
         }
         __syncthreads();                     /* previous coil's epilogue reads are done */
-        float2 *res = p2_fft<N, +1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j) - l * PITCH;
+        float2 *res = p2_fft<N, +1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j, l) - l * PITCH;
 #pragma unroll
         for (int o = 0; o < OUTS; ++o) {
             const int idx = threadIdx.x + o * (L * T);
@@ -542,7 +578,7 @@ p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const flo
         }
     }
     __syncthreads();
-    float2 *res = p2_fft<N, -1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j) - l * PITCH;
+    float2 *res = p2_fft<N, -1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j, l) - l * PITCH;
     const int a0 = blockIdx.x * L;
     float2 *out = tmp + (size_t)ch * N * nx + a0;
     for (int idx = threadIdx.x; idx < N * L; idx += L * T) {
@@ -574,7 +610,7 @@ p2_fwd_pass_b(const float2 *__restrict__ tmp, float2 *__restrict__ grid, const f
         v[q] = (a >= 0 && a < nx) ? src[a] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    float2 *res = p2_fft<N, -1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j) - l * PITCH;
+    float2 *res = p2_fft<N, -1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j, l) - l * PITCH;
     float2 *out = grid + (size_t)ch * N * N + c0;
     for (int idx = threadIdx.x; idx < N * L; idx += L * T) {
         const int r = idx / L, ll = idx % L;

@@ -318,34 +318,43 @@ __device__ __forceinline__ void gather_cell(float2 (&acc)[GS][CH], const GridLau
     const size_t spoke_bytes = (size_t)g.nro * g.nc_total * esz;
     const int samp_bytes = g.nc_total * (int)esz;
     const char *centre = samples + (size_t)(g.nro / 2) * samp_bytes;
+    /* the table entry of the next spoke is fetched while the current one is processed */
+    int k = c.kstart + first;
+    if (k >= g.npe) k -= g.npe;
+    float4 e = first < c.count ? __ldg(tab + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int pm = first < c.count ? __ldg(tpe + k) : 0;
     for (int it = first; it < c.count; it += step) {
-        int k = c.kstart + it;
-        if (k >= g.npe) k -= g.npe;
-        const float4 e = __ldg(tab + k);                 /* ct, st, 1/ct, 1/st */
-        float ax = xm * e.z, bx = xp * e.z, ay = ym * e.w, by = yp * e.w;
+        const float4 ec = e;                              /* ct, st, 1/ct, 1/st */
+        const int pmc = pm;
+        if (it + step < c.count) {
+            k += step;
+            if (k >= g.npe) k -= g.npe;
+            e = __ldg(tab + k); pm = __ldg(tpe + k);
+        }
+        float ax = xm * ec.z, bx = xp * ec.z, ay = ym * ec.w, by = yp * ec.w;
         float lo = fmaxf(fminf(ax, bx), fminf(ay, by)) - 1e-3f;
         float hi = fminf(fmaxf(ax, bx), fmaxf(ay, by)) + 1e-3f;
         lo = fmaxf(lo, -Rhif); hi = fminf(hi, Rhif);
         int r0 = (int)ceilf(lo), r1 = (int)floorf(hi);
         if (r0 > r1) continue;
-        const int pm = __ldg(tpe + k);
-        const int mask = GS > 1 ? (pm >> 24) : 1;
+        const int mask = GS > 1 ? (pmc >> 24) : 1;
         if (GS > 1 && mask == 0) continue;               /* spoke outside every window of a partial group */
-        const char *spoke = centre + (size_t)(pm & 0xffffff) * spoke_bytes;  /* sample ro = nro/2 of this spoke */
+        const char *spoke = centre + (size_t)(pmc & 0xffffff) * spoke_bytes;  /* sample ro = nro/2 of this spoke */
         for (int r = r0; r <= r1; ++r) {
             if (abs(r) < c.Rlo) continue;                /* annulus, tron.cu:501-502,512,521 */
             float rf = (float)r;
-            float dx = fma_ftz(e.x, rf, -Xf);            /* tron.cu:514,516 as compiled */
+            float dx = fma_ftz(ec.x, rf, -Xf);           /* tron.cu:514,516 as compiled */
             if (!(fabsf(dx) < W)) continue;
-            float dy = fma_ftz(e.y, rf, -Yf);
+            float dy = fma_ftz(ec.y, rf, -Yf);
             if (!(fabsf(dy) < W)) continue;
-            float w = kb_weight(dx, g.kb) * kb_weight(dy, g.kb);
-            if (!(w > 0.f)) continue;
+            /* the tap is live: start the sample load, evaluate the weight while it is in flight */
             int ridx = same ? r : (r * g.nro) / g.n;     /* tron.cu:517 */
-            float sdc = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);          /* tron.cu:412 */
-            w *= (r == 0) ? sdc + sdc : sdc;             /* both loops visit r = 0 */
             float2 v[CH];
             load_sample<CH, HALF>(v, spoke + (ptrdiff_t)ridx * samp_bytes);
+            float w = kb_weight(dx, g.kb) * kb_weight(dy, g.kb);
+            float sdc = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);          /* tron.cu:412 */
+            w *= (r == 0) ? sdc + sdc : sdc;             /* both loops visit r = 0 */
+            if (!(w > 0.f)) continue;                    /* the reference's wgt > 0 guard */
 #pragma unroll
             for (int s = 0; s < GS; ++s) {
                 if (GS == 1 || (mask >> s) & 1) {
@@ -455,12 +464,18 @@ __device__ __forceinline__ void grid_heavy_path(const GridLaunch &g, int block)
 
 /* one launch: the heavy-cell blocks come first (longest critical path), then the tiles */
 template <int CH, int GS, bool HALF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (CH * GS >= 16 ? 3 : 4))
 grid_gather_kernel(const GridLaunch g)
 {
     const int heavy_blocks = ((g.nheavy + 7) >> 3) * g.ngroups;
+    const long long t0 = g.dbg ? clock64() : 0;
     if ((int)blockIdx.x < heavy_blocks) grid_heavy_path<CH, GS, HALF>(g, blockIdx.x);
     else grid_tile_path<CH, GS, HALF>(g, blockIdx.x - heavy_blocks);
+    if (g.dbg) {                                          /* per-warp cycle counts (TRON_GRID_DEBUG) */
+        __syncwarp();
+        const long long t1 = clock64();
+        if ((threadIdx.x & 31) == 0) g.dbg[(size_t)blockIdx.x * 8 + (threadIdx.x >> 5)] = t1 - t0;
+    }
 }
 
 template <int CH, int GS>

@@ -128,12 +128,16 @@ static void plan_release(tron_plan *p)
     if (!p) return;
     cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
     fft_plan_free(p->fft);
-    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->heavy_cells);
+    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->heavy_cells); cudaFree(p->grid_dbg);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_in); cudaFree(p->d_out);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_in) cudaStreamDestroy(p->copy_in);
     if (p->copy_out) cudaStreamDestroy(p->copy_out);
     if (p->ev_in) cudaEventDestroy(p->ev_in);
+    if (p->s_grid) cudaStreamDestroy(p->s_grid);
+    if (p->s_fft) cudaStreamDestroy(p->s_fft);
+    for (int i = 0; i < 2; ++i) { if (p->ev_grid[i]) cudaEventDestroy(p->ev_grid[i]); if (p->ev_fft[i]) cudaEventDestroy(p->ev_fft[i]); }
+    if (p->ev_user) cudaEventDestroy(p->ev_user);
     for (int i = 0; i < 2; ++i) if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
     for (int i = 0; i < 4; ++i) if (p->ev_t[i]) cudaEventDestroy(p->ev_t[i]);
     delete p;
@@ -145,9 +149,11 @@ static int pick_batch(const tron_plan *p)
     const char *e = getenv("TRON_BATCH");
     if (e && atoi(e) > 0) return atoi(e) < p->nslices ? atoi(e) : p->nslices;
     size_t per = (size_t)p->nch * p->g.nxos * ((size_t)p->g.nxos + p->g.nx) * sizeof(float2);
-    size_t b = ((size_t)192 << 20) / (per ? per : 1);
+    /* launches of >= 32 slices reach the kernels' asymptotic throughput (profiles/r01_grid_only_timing.txt);
+     * the work buffers are bounded to ~1.5 GB of the 180 GB */
+    size_t b = ((size_t)1536 << 20) / (per ? per : 1);
     if (b < 1) b = 1;
-    if (b > 32) b = 32;
+    if (b > 64) b = 64;
     if ((int)b > p->nslices) b = p->nslices;
     return (int)b;
 }
@@ -173,6 +179,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     cudaGetDevice(&p->device);
     p->nch = g.coil_end - g.coil_begin;
     p->nslices = g.slice_end - g.slice_begin;
+    p->kb = make_kb(cfg->kernwidth);              /* plan-time polynomial fit, refmath.cuh */
     p->in_elem_bytes = cfg->half_in ? 4 : 8;
     p->out_elem_bytes = cfg->half_out ? 4 : 8;
     if (cfg->adjoint && cfg->sos_partial && g.nc > 1) p->out_elem_bytes = 4;
@@ -188,6 +195,17 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     PLAN_CUDA(cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking));
     PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+    {
+        int least = 0, greatest = 0;
+        PLAN_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        PLAN_CUDA(cudaStreamCreateWithPriority(&p->s_grid, cudaStreamNonBlocking, least));
+        PLAN_CUDA(cudaStreamCreateWithPriority(&p->s_fft, cudaStreamNonBlocking, greatest));
+        for (int i = 0; i < 2; ++i) {
+            PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_grid[i], cudaEventDisableTiming));
+            PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_fft[i], cudaEventDisableTiming));
+        }
+        PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_user, cudaEventDisableTiming));
+    }
     for (int i = 0; i < 4; ++i) PLAN_CUDA(cudaEventCreate(&p->ev_t[i]));
 
     const int n = g.nxos;
@@ -220,7 +238,12 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         p->batch = ((p->batch + p->tabs.gs - 1) / p->tabs.gs) * p->tabs.gs;
     }
     p->stage_timing = getenv("TRON_STAGE_TIMING") != nullptr;
-    PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)p->batch * p->nch * n * n * sizeof(float2)));
+    if (cfg->adjoint && getenv("TRON_GRID_DEBUG")) {
+        PLAN_CUDA(cudaMalloc(&p->grid_dbg, (size_t)8 * 65536 * 8 * sizeof(long long)));
+        PLAN_CUDA(cudaMemset(p->grid_dbg, 0, (size_t)8 * 65536 * 8 * sizeof(long long)));
+    }
+    p->overlap = cfg->adjoint && p->nslices > p->batch && getenv("TRON_OVERLAP") != nullptr;   /* measured slower on B200: off */
+    PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)(p->overlap ? 2 : 1) * p->batch * p->nch * n * n * sizeof(float2)));
     PLAN_CUDA(cudaMalloc(&p->d_tmp, (size_t)p->batch * p->nch * n * g.nx * sizeof(float2)));
     PLAN_CUDA(cudaStreamSynchronize(p->stream));
 #undef PLAN_TRY
@@ -258,12 +281,13 @@ static GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, fl
     L.n = g.nxos; L.nro = g.nro; L.npe = p->tabs.npe; L.gs = p->tabs.gs; L.ngroups = 0;
     L.nc_total = g.nc * g.nt; L.ch0 = g.coil_begin; L.nch = p->nch;
     L.z0 = z0; L.nslices = nb; L.slide = g.prof_slide;
-    L.kb = make_kb(p->cfg.kernwidth);
+    L.kb = p->kb;
     /* tron.cu:408-409 and 532 */
     L.sdc_a = (2.f - 2.f / (float)g.npe1work) / (float)g.nro;
     L.sdc_b = 1.f / (float)g.npe1work;
     L.scale = 1.f / (float)g.nxos / (float)g.npe1work;
     L.half_in = p->cfg.half_in;
+    L.dbg = p->grid_dbg;
     return L;
 }
 
@@ -274,32 +298,101 @@ static int adjoint_mode(const tron_plan *p)
     return p->cfg.sos_partial ? 3 : 0;
 }
 
-/* one batch of adjoint slices, all on stream s */
-static int run_adjoint_batch(tron_plan *p, void *d_out, const void *d_in, int z0, int nb, cudaStream_t s)
+/* the two halves of one batch of adjoint slices */
+static int launch_batch_grid(tron_plan *p, const void *d_in, float2 *d_grid, int z0, int nb, cudaStream_t s)
+{
+    GridLaunch L = make_grid_launch(p, d_in, d_grid, z0, nb);
+    p->last_launches += 1;
+    return launch_grid(L, s);
+}
+
+static int launch_batch_fft(tron_plan *p, void *d_out, const float2 *d_grid, int z0, int nb, cudaStream_t s)
 {
     const tron_geometry &g = p->g;
-    GridLaunch L = make_grid_launch(p, d_in, p->d_grid, z0, nb);
-    if (p->stage_timing) cudaEventRecord(p->ev_t[0], s);
-    int rc = launch_grid(L, s);
-    if (rc) return rc;
-    if (p->stage_timing) cudaEventRecord(p->ev_t[1], s);
     AdjFftLaunch a;
-    a.grid = p->d_grid; a.tmp = p->d_tmp; a.deapod = p->deapod_adj;
+    a.grid = d_grid; a.tmp = p->d_tmp; a.deapod = p->deapod_adj;
     a.nslices = nb; a.nch = p->nch; a.nc_total = g.nc * g.nt; a.ch0 = g.coil_begin;
     a.mode = adjoint_mode(p); a.half_out = p->cfg.half_out;
     size_t per = (size_t)g.nx * g.ny * (a.mode == 2 ? (size_t)g.nc : 1);
     a.out = (char *)d_out + (size_t)z0 * per * p->out_elem_bytes;
-    rc = launch_adj_fft(p->fft, a, s);
-    p->last_launches += 3;
-    if (p->stage_timing && !rc) {               /* diagnostic mode: serialises host and device */
-        cudaEventRecord(p->ev_t[2], s);
-        cudaEventSynchronize(p->ev_t[2]);
-        float t0 = 0, t1 = 0;
-        cudaEventElapsedTime(&t0, p->ev_t[0], p->ev_t[1]);
-        cudaEventElapsedTime(&t1, p->ev_t[1], p->ev_t[2]);
-        p->last_ms[0] += t0; p->last_ms[1] += t1;
+    p->last_launches += 2;
+    return launch_adj_fft(p->fft, a, s);
+}
+
+/* All adjoint slices of the plan.  Gridding (instruction-issue bound) runs on a low-priority
+ * stream, the FFT passes (shared-memory / HBM bound) of the previous batch on a high-priority
+ * one, so blocks of both kinds are resident on the SMs at the same time; the oversampled grid is
+ * double buffered.  Host mode (h_in != NULL) uploads each spoke once, in the order the batches
+ * need them, and downloads trail the FFT stream.  `user` (device mode) is made to wait for the
+ * start of its own prior work and for the end of ours. */
+static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStream_t user,
+                           const void *h_in, void *h_out)
+{
+    const tron_geometry &g = p->g;
+    const bool host = h_in != nullptr;
+    const bool overlap = p->overlap && !p->stage_timing;
+    cudaStream_t sg = overlap ? p->s_grid : (host ? p->stream : user);
+    cudaStream_t sf = overlap ? p->s_fft : sg;
+    if (!host && overlap) {
+        TRON_CUDA(cudaEventRecord(p->ev_user, user));
+        TRON_CUDA(cudaStreamWaitEvent(sg, p->ev_user, 0));
+        TRON_CUDA(cudaStreamWaitEvent(sf, p->ev_user, 0));
     }
-    return rc;
+    const size_t spoke_bytes = (size_t)g.nc * g.nt * g.nro * p->in_elem_bytes;
+    const size_t slice_out_bytes = (size_t)g.nx * g.ny * (p->cfg.per_coil_out ? (size_t)g.nc : 1) * p->out_elem_bytes;
+    const size_t grid_elems = (size_t)p->batch * p->nch * g.nxos * g.nxos;
+    size_t spokes_up = 0;
+    int i = 0;
+    for (int z0 = 0; z0 < p->nslices; z0 += p->batch, i ^= 1) {
+        const int nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
+        float2 *gridbuf = p->d_grid + (overlap ? (size_t)i * grid_elems : 0);
+        if (host) {
+            size_t need = (size_t)(z0 + nb - 1) * g.prof_slide + g.npe1work;
+            if (need > spokes_up) {
+                TRON_CUDA(cudaMemcpyAsync((char *)d_in + spokes_up * spoke_bytes,
+                                          (const char *)h_in + spokes_up * spoke_bytes,
+                                          (need - spokes_up) * spoke_bytes, cudaMemcpyHostToDevice, p->copy_in));
+                spokes_up = need;
+                TRON_CUDA(cudaEventRecord(p->ev_in, p->copy_in));
+                TRON_CUDA(cudaStreamWaitEvent(sg, p->ev_in, 0));
+            }
+        }
+        if (overlap) TRON_CUDA(cudaStreamWaitEvent(sg, p->ev_fft[i], 0));   /* buffer i free again */
+        if (p->stage_timing) cudaEventRecord(p->ev_t[0], sg);
+        int rc = launch_batch_grid(p, d_in, gridbuf, z0, nb, sg);
+        if (rc) return rc;
+        if (p->stage_timing) cudaEventRecord(p->ev_t[1], sg);
+        if (overlap) {
+            TRON_CUDA(cudaEventRecord(p->ev_grid[i], sg));
+            TRON_CUDA(cudaStreamWaitEvent(sf, p->ev_grid[i], 0));
+        }
+        rc = launch_batch_fft(p, d_out, gridbuf, z0, nb, sf);
+        if (rc) return rc;
+        if (p->stage_timing) {                     /* diagnostic mode: serialises host and device */
+            cudaEventRecord(p->ev_t[2], sf);
+            cudaEventSynchronize(p->ev_t[2]);
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, p->ev_t[0], p->ev_t[1]);
+            cudaEventElapsedTime(&t1, p->ev_t[1], p->ev_t[2]);
+            p->last_ms[0] += t0; p->last_ms[1] += t1;
+        }
+        if (overlap || host) TRON_CUDA(cudaEventRecord(p->ev_fft[i], sf));
+        if (host) {
+            TRON_CUDA(cudaStreamWaitEvent(p->copy_out, p->ev_fft[i], 0));
+            TRON_CUDA(cudaMemcpyAsync((char *)h_out + (size_t)z0 * slice_out_bytes,
+                                      (char *)d_out + (size_t)z0 * slice_out_bytes,
+                                      (size_t)nb * slice_out_bytes, cudaMemcpyDeviceToHost, p->copy_out));
+        }
+    }
+    if (host) {
+        TRON_CUDA(cudaStreamSynchronize(p->copy_out));
+        TRON_CUDA(cudaStreamSynchronize(sf));
+        TRON_CUDA(cudaStreamSynchronize(sg));
+    } else if (overlap) {
+        TRON_CUDA(cudaEventRecord(p->ev_user, sf));
+        TRON_CUDA(cudaStreamWaitEvent(user, p->ev_user, 0));
+    }
+    return TRON_OK;
 }
 
 static int run_forward(tron_plan *p, void *d_out, const void *d_in, cudaStream_t s)
@@ -314,7 +407,7 @@ static int run_forward(tron_plan *p, void *d_out, const void *d_in, cudaStream_t
     d.samples = d_out; d.grid = p->d_grid; d.cs = p->tabs.cs_lin;
     d.n = g.nxos; d.nro = g.nro; d.npe = g.npe1work;
     d.nc_total = g.nc * g.nt; d.ch0 = g.coil_begin; d.nch = p->nch;
-    d.kb = make_kb(p->cfg.kernwidth); d.half_out = p->cfg.half_out;
+    d.kb = p->kb; d.half_out = p->cfg.half_out;
     rc = launch_degrid(d, s);
     p->last_launches += 3;
     return rc;
@@ -328,12 +421,7 @@ extern "C" int tron_recon_device(tron_plan *p, void *d_out, const void *d_in, vo
     p->last_launches = 0;
     p->last_ms[0] = p->last_ms[1] = p->last_ms[2] = 0.f;
     if (!p->cfg.adjoint) return run_forward(p, d_out, d_in, s);
-    for (int z0 = 0; z0 < p->nslices; z0 += p->batch) {
-        int nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
-        int rc = run_adjoint_batch(p, d_out, d_in, z0, nb, s);
-        if (rc) return rc;
-    }
-    return TRON_OK;
+    return run_adjoint_all(p, d_out, d_in, s, nullptr, nullptr);
 }
 
 extern "C" int tron_recon_host(tron_plan *p, void *h_out, const void *h_in)
@@ -343,7 +431,7 @@ extern "C" int tron_recon_host(tron_plan *p, void *h_out, const void *h_in)
     if (!p->d_in) TRON_CUDA(cudaMalloc(&p->d_in, p->in_bytes));
     if (!p->d_out) TRON_CUDA(cudaMalloc(&p->d_out, p->out_bytes));
     p->last_launches = 0;
-    const tron_geometry &g = p->g;
+    p->last_ms[0] = p->last_ms[1] = p->last_ms[2] = 0.f;
     if (!p->cfg.adjoint) {
         TRON_CUDA(cudaMemcpyAsync(p->d_in, h_in, p->in_bytes, cudaMemcpyHostToDevice, p->stream));
         int rc = run_forward(p, p->d_out, p->d_in, p->stream);
@@ -352,34 +440,7 @@ extern "C" int tron_recon_host(tron_plan *p, void *h_out, const void *h_in)
         TRON_CUDA(cudaStreamSynchronize(p->stream));
         return TRON_OK;
     }
-    /* adjoint: upload each spoke once, in the order the batches need them;
-     * compute waits for its window; downloads trail the compute stream */
-    const size_t spoke_bytes = (size_t)g.nc * g.nt * g.nro * p->in_elem_bytes;
-    const size_t slice_out_bytes = (size_t)g.nx * g.ny * (p->cfg.per_coil_out ? (size_t)g.nc : 1) * p->out_elem_bytes;
-    size_t spokes_up = 0;
-    int parity = 0;
-    for (int z0 = 0; z0 < p->nslices; z0 += p->batch, parity ^= 1) {
-        int nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
-        size_t need = (size_t)(z0 + nb - 1) * g.prof_slide + g.npe1work;
-        if (need > spokes_up) {
-            TRON_CUDA(cudaMemcpyAsync((char *)p->d_in + spokes_up * spoke_bytes,
-                                      (const char *)h_in + spokes_up * spoke_bytes,
-                                      (need - spokes_up) * spoke_bytes, cudaMemcpyHostToDevice, p->copy_in));
-            spokes_up = need;
-            TRON_CUDA(cudaEventRecord(p->ev_in, p->copy_in));
-            TRON_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in, 0));
-        }
-        int rc = run_adjoint_batch(p, p->d_out, p->d_in, z0, nb, p->stream);
-        if (rc) return rc;
-        TRON_CUDA(cudaEventRecord(p->ev_done[parity], p->stream));
-        TRON_CUDA(cudaStreamWaitEvent(p->copy_out, p->ev_done[parity], 0));
-        TRON_CUDA(cudaMemcpyAsync((char *)h_out + (size_t)z0 * slice_out_bytes,
-                                  (char *)p->d_out + (size_t)z0 * slice_out_bytes,
-                                  (size_t)nb * slice_out_bytes, cudaMemcpyDeviceToHost, p->copy_out));
-    }
-    TRON_CUDA(cudaStreamSynchronize(p->copy_out));
-    TRON_CUDA(cudaStreamSynchronize(p->stream));
-    return TRON_OK;
+    return run_adjoint_all(p, p->d_out, p->d_in, nullptr, h_in, h_out);
 }
 
 /* ---------------- stage-level entry points ---------------- */
@@ -414,7 +475,7 @@ extern "C" int tron_degrid_device(tron_plan *p, void *d_samples, const void *d_g
     d.samples = d_samples; d.grid = p->d_grid; d.cs = p->tabs.cs_lin;
     d.n = g.nxos; d.nro = g.nro; d.npe = g.npe1work;
     d.nc_total = g.nc * g.nt; d.ch0 = 0; d.nch = p->nch;
-    d.kb = make_kb(p->cfg.kernwidth); d.half_out = p->cfg.half_out;
+    d.kb = p->kb; d.half_out = p->cfg.half_out;
     return launch_degrid(d, s);
 }
 
@@ -426,6 +487,16 @@ extern "C" int tron_plan_last_stage_ms(tron_plan *p, float ms[3])
 }
 
 extern "C" int tron_plan_last_launches(const tron_plan *p) { return p ? p->last_launches : 0; }
+
+/* diagnostic: copy out the per-warp cycle counts of the last gridding launch (TRON_GRID_DEBUG) */
+extern "C" int tron_plan_grid_debug(tron_plan *p, long long *h_cycles, int nwarps)
+{
+    if (!p || !p->grid_dbg) { set_error("plan was not created with TRON_GRID_DEBUG set"); return TRON_EINVAL; }
+    if (nwarps > 8 * 65536 * 8) nwarps = 8 * 65536 * 8;
+    TRON_CUDA(cudaDeviceSynchronize());
+    TRON_CUDA(cudaMemcpy(h_cycles, p->grid_dbg, (size_t)nwarps * sizeof(long long), cudaMemcpyDeviceToHost));
+    return TRON_OK;
+}
 
 /* pinned host memory for ra_read_pinned (ra.c is plain C and does not see cudart) */
 extern "C" int tron_pinned_alloc(void **p, size_t bytes)

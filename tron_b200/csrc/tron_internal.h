@@ -43,6 +43,7 @@ struct GridLaunch {               /* everything the gridding kernel needs */
     KbParams kb;
     float sdc_a, sdc_b, scale;
     int half_in;
+    long long *dbg;               /* optional per-warp cycle counts [blocks][8] */
 };
 
 struct DegridLaunch {
@@ -110,11 +111,16 @@ struct tron_plan {
     int batch = 1;
     cudaStream_t stream = nullptr;       /* compute */
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t s_grid = nullptr, s_fft = nullptr;   /* low / high priority compute streams */
+    cudaEvent_t ev_grid[2] = {nullptr, nullptr}, ev_fft[2] = {nullptr, nullptr}, ev_user = nullptr;
+    int overlap = 0;                     /* gridding of batch k+1 overlaps the FFT passes of batch k */
     cudaEvent_t ev_in = nullptr, ev_done[2] = {nullptr, nullptr}, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    tronb::KbParams kb;
     tronb::SpokeTables tabs;
     tronb::FftPlan fft;
     float *deapod_adj = nullptr, *deapod_fwd = nullptr;
     int *tile_order = nullptr, *heavy_cells = nullptr;
+    long long *grid_dbg = nullptr;       /* TRON_GRID_DEBUG: per-warp cycles of the last gridding launch */
     int nheavy = 0, heavy_r2 = -1;
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
     void *d_in = nullptr, *d_out = nullptr;         /* device staging for the host API */
