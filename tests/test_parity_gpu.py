@@ -404,3 +404,59 @@ def test_full_size_linearity_and_shard_consistency(lib):
         rss = p.recon_host(x)
     want = np.sqrt((np.abs(ax.reshape(-1, 6).astype(np.complex128)) ** 2).sum(axis=1))
     assert rel_l2(rss.real, want) <= 1e-6
+
+
+# ------------------------------------------------------------------ many channels (lanes = channels kernel)
+@pytest.mark.parametrize("nc,flags", [
+    (16, dict(adjoint=True, golden=True, undersamp=0.5, prof_slide=5)),          # 4-slice tap sharing, half-warp mode
+    (32, dict(adjoint=True, golden=True)),                                       # one slice, 32 lanes = 32 channels
+    (32, dict(adjoint=True, prof_slide=40, undersamp=0.5)),                      # linear angles, sliding, shared table
+    (64, dict(adjoint=True, golden=True, kernwidth=3.0)),                        # two channels per lane
+    (48, dict(adjoint=True, golden=True, gridos=1.5)),                           # ragged last channel chunk
+    (32, dict(adjoint=True, golden=True, undersamp=0.25, prof_slide=3, skip_angles=9)),
+])
+def test_wide_channel_gridding_vs_reference(lib, reflib_wide, nc, flags):
+    import tron_b200 as t
+    torch_cuda()
+    dims = [nc, 1, 64, 96, 1]
+    h_in = synth_complex((int(np.prod(dims)),), stream=200 + nc)
+    want = run_ref(reflib_wide, dims, flags, h_in)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        got = p.recon_host(h_in)
+    assert rel_l2(got, want) <= TOL_F32, rel_l2(got, want)
+    os.environ["TRON_NO_WIDE"] = "1"          # the thread-per-cell kernel must agree with the wide one
+    try:
+        import importlib
+        with t.Plan(flags_to_cfg(dims, flags, per_coil_out=True)) as p:
+            a = p.recon_host(h_in)
+    finally:
+        del os.environ["TRON_NO_WIDE"]
+    with t.Plan(flags_to_cfg(dims, flags, per_coil_out=True)) as p:
+        b = p.recon_host(h_in)
+    assert rel_l2(b, a) <= 2e-6
+
+
+def test_wide_channel_index_map_bit_exact(lib, reflib_wide):
+    """Indicator probes through the wide kernel: 32 samples per launch, support must equal the reference's."""
+    import tron_b200 as t
+    torch = torch_cuda()
+    nro, npe, skip, nchan = 32, 10, 4, 32
+    total = nro * npe
+    for base in range(0, total, nchan):
+        ids = [min(base + c, total - 1) for c in range(nchan)]
+        mine, want = _indicator_probe_grid(t, torch, reflib_wide, nro, npe, nchan, True, 2.0, 2.0, skip, ids)
+        assert np.array_equal(mine != 0, want != 0), "index map differs for samples %s" % ids
+
+
+def test_wide_channel_fp16_storage(lib):
+    import tron_b200 as t
+    torch_cuda()
+    dims = [32, 1, 64, 80, 1]
+    flags = dict(adjoint=True, golden=True, undersamp=0.5, prof_slide=16)
+    h_in = synth_complex((int(np.prod(dims)),), stream=210)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        want = p.recon_host(h_in)
+    h16 = h_in.view(np.float32).astype(np.float16)
+    with t.Plan(flags_to_cfg(dims, flags, half_in=True)) as p:
+        got = p.recon_host(h16)
+    assert rel_l2(got, want) <= TOL_F16

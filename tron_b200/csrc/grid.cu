@@ -44,6 +44,7 @@
 #include "tron_internal.h"
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 #include <utility>
 #include <vector>
 
@@ -496,6 +497,8 @@ int launch_grid(const GridLaunch &g, cudaStream_t s)
     size_t esz = g.half_in ? 4 : 8;
     bool aligned = (((uintptr_t)g.samples) % (2 * esz) == 0) && (g.nc_total % 2 == 0) && (g.ch0 % 2 == 0);
     if (g.nslices <= 0 || g.nch <= 0) return 0;
+    const bool no_wide = getenv("TRON_NO_WIDE") != nullptr;      /* diagnostic switch, read per launch */
+    if (!no_wide && grid_wide_applicable(g)) return launch_grid_wide(g, s);   /* nc >= 16: lanes = channels */
     if (g.gs == 4) {                                      /* sliding windows share taps across 4 slices */
         if (!aligned || g.nch % 2) return launch_grid_cg<1, 4>(g, s);
         if (g.nch % 6 == 0) return launch_grid_cg<6, 4>(g, s);

@@ -1,0 +1,321 @@
+/*
+ * grid_wide.cu -- gridding for many receive channels (nc = 16, 32, 64, ...): lanes = channels.
+ *
+ * Same operator and the same tap set as grid.cu (reference: precompensate + gridradial2d,
+ * /root/reference/src/tron.cu:405-416, 465-536); different decomposition.  With one thread per
+ * cell every tap costs nc scattered 8-byte loads per thread; here a warp owns a block of 4 x 2
+ * cells and works in two phases:
+ *
+ *   A  lanes = spokes of the block's angular window.  Each lane walks the radii of its spoke that
+ *      fall into the block's support box, evaluates the reference predicate for the 8 cells
+ *      (fused fma, annulus, r = 0 twice -- refmath.cuh), the separable Kaiser-Bessel weights
+ *      (4 + 2 evaluations serve 8 cells) and the density ramp, and appends
+ *      (sample offset, 8 weights, slice mask) to a per-warp list in shared memory.
+ *   B  lanes = channels.  For every list entry the warp loads the sample's channels with one
+ *      coalesced request (256 B for 32 channels) and feeds the 8 cells' accumulators with packed
+ *      FFMA2s: each sample is fetched once per block instead of once per cell (3.7x fewer
+ *      requests), and every request is a full cache line.
+ *
+ * The list is drained whenever it could overflow, so blocks near DC (thousands of taps) need no
+ * special path.  Sliding golden-angle windows share phase A across GS = 4 slices like grid.cu.
+ * nc = 16 runs two entries per iteration (one per half-warp) and folds the halves at the end;
+ * nc = 64 keeps two channels per lane.  Output: planar grid[slice][ch][row][col]; a lane writes
+ * whole 32-byte sectors (4 cells of a row) of its channel plane.
+ */
+#include "tron_internal.h"
+
+namespace tronb {
+
+#define PI_F 3.14159274101257324219f
+#define WCAP 96                       /* list entries per warp */
+
+struct __align__(16) WideList {
+    float4 wa[WCAP];                  /* weights of cells (0..3, row 0) */
+    float4 wb[WCAP];                  /* weights of cells (0..3, row 1) */
+    int off[WCAP];                    /* sample offset in elements from the group's channel base */
+    int mask[WCAP];                   /* slices of the group whose window holds the spoke */
+};
+
+__device__ __forceinline__ void ffma2w(float2 &acc, float w, float2 v)
+{
+    unsigned long long a = *reinterpret_cast<unsigned long long *>(&acc);
+    float2 ww = make_float2(w, w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(a)
+        : "l"(*reinterpret_cast<unsigned long long *>(&ww)), "l"(*reinterpret_cast<unsigned long long *>(&v)));
+    acc = *reinterpret_cast<float2 *>(&a);
+}
+
+template <bool HALF>
+__device__ __forceinline__ float2 load_chan(const void *base, size_t idx)
+{
+    if (HALF) {
+        unsigned raw = __ldg((const unsigned *)base + idx);
+        return __half22float2(*reinterpret_cast<__half2 *>(&raw));
+    }
+    return __ldg((const float2 *)base + idx);
+}
+
+/* phase B: consume the list.  LPC = lanes per entry (32, or 16: two entries per iteration). */
+template <int LPC, int NCHUNK, int GS, bool HALF>
+__device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], const WideList &L, int cnt,
+                                           const void *samples, int lane, int nvalid)
+{
+    constexpr int EPI = 32 / LPC;                    /* entries per iteration */
+    const int sub = lane / LPC, ch = lane % LPC;
+    __syncwarp();
+    for (int e0 = 0; e0 < cnt; e0 += 2 * EPI) {      /* two iterations in flight */
+        const int ea = e0 + sub, eb = e0 + EPI + sub;
+        const bool va = ea < cnt, vb = eb < cnt;
+        const int offa = va ? L.off[ea] : 0, offb = vb ? L.off[eb] : 0;
+        float2 xa[NCHUNK], xb[NCHUNK];
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+            const bool cok = c * 32 + ch < nvalid;       /* channels beyond the plan's last one are not read */
+            xa[c] = va && cok ? load_chan<HALF>(samples, (size_t)offa + c * 32 + ch) : make_float2(0.f, 0.f);
+            xb[c] = vb && cok ? load_chan<HALF>(samples, (size_t)offb + c * 32 + ch) : make_float2(0.f, 0.f);
+        }
+        if (va) {
+            const float4 p = L.wa[ea], q = L.wb[ea];
+            const int m = GS > 1 ? L.mask[ea] : 1;
+            const float w[8] = { p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int s = 0; s < GS; ++s)
+                if (GS == 1 || (m >> s) & 1) {
+#pragma unroll
+                    for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ffma2w(acc[c][s][i], w[i], xa[c]);
+                }
+        }
+        if (vb) {
+            const float4 p = L.wa[eb], q = L.wb[eb];
+            const int m = GS > 1 ? L.mask[eb] : 1;
+            const float w[8] = { p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int s = 0; s < GS; ++s)
+                if (GS == 1 || (m >> s) & 1) {
+#pragma unroll
+                    for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ffma2w(acc[c][s][i], w[i], xb[c]);
+                }
+        }
+    }
+    __syncwarp();
+}
+
+template <int LPC, int NCHUNK, int GS, bool HALF>
+__global__ void __launch_bounds__(256)
+grid_wide_kernel(const GridLaunch g)
+{
+    __shared__ WideList lists[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WideList &L = lists[warp];
+    const int n = g.n;
+    const int tiles_x = (n + 15) >> 4;
+    const int rank = blockIdx.x / g.ngroups, grp = blockIdx.x - rank * g.ngroups;
+    const int tile = __ldg(g.tile_order + rank);
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int chan0 = blockIdx.y * (LPC * NCHUNK);           /* first plan-local channel of this CTA */
+
+    const int ug = g.z0 / GS + grp;
+    const int tabi = g.tab_per_slice ? ug : 0;
+    const float4 *tab = g.tab_cs + (size_t)tabi * g.npe;
+    const int *tpe = g.tab_pe + (size_t)tabi * g.npe;
+    const int *lut = g.lut + (size_t)tabi * (g.nbins + 1);
+    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
+    const char *samples = (const char *)g.samples
+        + ((size_t)ug * GS * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chan0)) * esz;
+
+    const float W = g.kb.W;
+    const bool same = g.nro == g.n;
+    const float Rmaxf = (float)(n / 2 - 1);
+    const float lut_scale = (float)g.nbins / PI_F;
+
+    for (int bi = warp; bi < 32; bi += 8) {
+        const int x0 = tx * 16 + (bi & 3) * 4, y0 = ty * 16 + (bi >> 2) * 2;
+        if (x0 >= n || y0 >= n) continue;
+        const int X0 = x0 - n / 2, Y0 = y0 - n / 2;
+
+        /* annulus of the 8 cells (cell c = cy*4 + cx), broadcast from lanes 0..7 */
+        int myband = 0;
+        if (lane < 8) myband = __ldg(g.cells + (size_t)(y0 + (lane >> 2)) * n + x0 + (lane & 3)).x;
+        int band[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) band[c] = __shfl_sync(0xffffffffu, myband, c);
+        bool dead = true;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dead = dead && ((band[c] & 0xffff) > (band[c] >> 16));
+
+        float2 acc[NCHUNK][GS][8];
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+            for (int s = 0; s < GS; ++s)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[c][s][i] = make_float2(0.f, 0.f);
+
+        if (!dead) {
+            /* spokes whose line passes within reach of the block (centre (X0+1.5, Y0+0.5), half diagonal 1.59) */
+            const float Xc = (float)X0 + 1.5f, Yc = (float)Y0 + 0.5f;
+            const float Rc = sqrtf(Xc * Xc + Yc * Yc);
+            const float reach = W * 1.41421368f + 1.59f + 2e-3f;
+            const float xr = reach / fmaxf(Rc, 1e-6f);
+            int kstart = 0, count = g.npe;
+            if (xr <= 0.7f) {
+                float T = atan2f(Yc, Xc);
+                if (T < 0.f) T += PI_F;
+                if (T >= PI_F) T -= PI_F;
+                const float delta = xr * fmaf(0.25f * xr, xr, 1.0f) + 2e-4f;
+                int b0 = (int)floorf((T - delta) * lut_scale);
+                int b1 = (int)floorf((T + delta) * lut_scale);
+                if (b1 - b0 + 1 < g.nbins) {
+                    bool wrap = false;
+                    if (b0 < 0) { b0 += g.nbins; wrap = true; }
+                    if (b1 >= g.nbins) { b1 -= g.nbins; wrap = true; }
+                    const int ks = __ldg(lut + b0), ke = __ldg(lut + b1 + 1);
+                    kstart = ks;
+                    count = wrap ? (g.npe - ks) + ke : ke - ks;
+                }
+            }
+            const float xlo = (float)X0 - W, xhi = (float)(X0 + 3) + W;
+            const float ylo = (float)Y0 - W, yhi = (float)(Y0 + 1) + W;
+            int cnt = 0;
+
+            for (int it0 = 0; it0 < count; it0 += 32) {
+                /* phase A: lane = spoke */
+                const int it = it0 + lane;
+                const bool have = it < count;
+                int k = kstart + (have ? it : 0);
+                if (k >= g.npe) k -= g.npe;
+                const float4 e = __ldg(tab + k);                 /* ct, st, 1/ct, 1/st */
+                const int pm = __ldg(tpe + k);
+                float ax = xlo * e.z, bx = xhi * e.z, ay = ylo * e.w, by = yhi * e.w;
+                float lo = fmaxf(fminf(ax, bx), fminf(ay, by)) - 1e-3f;
+                float hi = fminf(fmaxf(ax, bx), fmaxf(ay, by)) + 1e-3f;
+                /* two-sided clamps: with ct or st near 0 the bounds reach +-1e18 and the int length would wrap */
+                lo = fminf(fmaxf(lo, -Rmaxf), Rmaxf + 1.f); hi = fmaxf(fminf(hi, Rmaxf), -Rmaxf - 1.f);
+                const int r0 = (int)ceilf(lo);
+                int len = (int)floorf(hi) - r0 + 1;
+                if (!have || (GS > 1 && (pm >> 24) == 0)) len = 0;
+                const int maxlen = __reduce_max_sync(0xffffffffu, len);
+                const int spoke_off = (pm & 0xffffff) * g.nro + g.nro / 2;     /* sample index of ro = nro/2 */
+                for (int i = 0; i < maxlen; ++i) {
+                    const int r = r0 + i;
+                    const float rf = (float)r;
+                    const int ar = abs(r);
+                    float w8[8];
+                    bool any = false;
+                    if (i < len) {
+                        float wx[4], wy[2];
+#pragma unroll
+                        for (int cx = 0; cx < 4; ++cx) {
+                            const float dx = fma_ftz(e.x, rf, -(float)(X0 + cx));      /* tron.cu:514 as compiled */
+                            wx[cx] = fabsf(dx) < W ? kb_weight(dx, g.kb) : 0.f;
+                        }
+                        const int ridx = same ? r : (r * g.nro) / g.n;                  /* tron.cu:517 */
+                        float f = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);           /* tron.cu:412 */
+                        if (r == 0) f += f;                                              /* r = 0 visited twice */
+#pragma unroll
+                        for (int cy = 0; cy < 2; ++cy) {
+                            const float dy = fma_ftz(e.y, rf, -(float)(Y0 + cy));
+                            wy[cy] = fabsf(dy) < W ? kb_weight(dy, g.kb) * f : 0.f;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const bool inband = ar >= (band[c] & 0xffff) && ar <= (band[c] >> 16);
+                            const float w = inband ? wx[c & 3] * wy[c >> 2] : 0.f;
+                            w8[c] = w > 0.f ? w : 0.f;
+                            any = any || w > 0.f;
+                        }
+                    }
+                    const unsigned hit = __ballot_sync(0xffffffffu, any);
+                    if (any) {
+                        const int slot = cnt + __popc(hit & ((1u << lane) - 1u));
+                        const int ridx = same ? r : (r * g.nro) / g.n;
+                        L.wa[slot] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+                        L.wb[slot] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                        L.off[slot] = (spoke_off + ridx) * g.nc_total;
+                        L.mask[slot] = pm >> 24;
+                    }
+                    cnt += __popc(hit);
+                    if (cnt + 32 > WCAP) {                       /* phase B: lanes = channels */
+                        wide_drain<LPC, NCHUNK, GS, HALF>(acc, L, cnt, samples, lane, g.nch - chan0);
+                        cnt = 0;
+                    }
+                }
+            }
+            wide_drain<LPC, NCHUNK, GS, HALF>(acc, L, cnt, samples, lane, g.nch - chan0);
+        }
+
+        /* fold the two half-warps (nc = 16 mode), then every lane writes its channel plane */
+        if (LPC == 16) {
+#pragma unroll
+            for (int s = 0; s < GS; ++s)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[0][s][i].x += __shfl_down_sync(0xffffffffu, acc[0][s][i].x, 16);
+                    acc[0][s][i].y += __shfl_down_sync(0xffffffffu, acc[0][s][i].y, 16);
+                }
+        }
+        if (lane < LPC) {
+            const size_t plane = (size_t)n * n;
+            const int zg = ug * GS;
+#pragma unroll
+            for (int s = 0; s < GS; ++s) {
+                const int zl = zg + s - g.z0;
+                if (zl < 0 || zl >= g.nslices) continue;
+#pragma unroll
+                for (int c = 0; c < NCHUNK; ++c) {
+                    const int ch = chan0 + c * 32 + lane;
+                    if (ch >= g.nch) continue;
+                    float2 *out = g.grid + ((size_t)zl * g.nch + ch) * plane + (size_t)y0 * n + x0;
+#pragma unroll
+                    for (int cy = 0; cy < 2; ++cy) {
+                        float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)cy * n);
+                        const float2 *a = &acc[c][s][cy * 4];
+                        o4[0] = make_float4(a[0].x * g.scale, a[0].y * g.scale, a[1].x * g.scale, a[1].y * g.scale);
+                        o4[1] = make_float4(a[2].x * g.scale, a[2].y * g.scale, a[3].x * g.scale, a[3].y * g.scale);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int LPC, int NCHUNK, int GS>
+static int launch_wide(GridLaunch g, cudaStream_t s)
+{
+    int tiles = ((g.n + 15) / 16) * ((g.n + 15) / 16);
+    g.ngroups = (g.z0 + g.nslices - 1) / GS - g.z0 / GS + 1;
+    int per_cta = LPC * NCHUNK;
+    dim3 grid(tiles * g.ngroups, (g.nch + per_cta - 1) / per_cta);
+    if (g.half_in) grid_wide_kernel<LPC, NCHUNK, GS, true><<<grid, 256, 0, s>>>(g);
+    else           grid_wide_kernel<LPC, NCHUNK, GS, false><<<grid, 256, 0, s>>>(g);
+    TRON_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool grid_wide_applicable(const GridLaunch &g)
+{
+    /* nc = 16 is faster on the thread-per-cell kernel (measured: 9.3 vs 18.3 us/slice on cfg4) */
+    if (g.nch < 32 || g.nch % 16 != 0) return false;
+    if (g.n % 4 != 0) return false;
+    if (g.gs != 1 && g.gs != 4) return false;
+    return true;
+}
+
+int launch_grid_wide(const GridLaunch &g, cudaStream_t s)
+{
+    if (g.nslices <= 0 || g.nch <= 0) return 0;
+    if (g.gs == 4) {
+        if (g.nch == 16) return launch_wide<16, 1, 4>(g, s);
+        return launch_wide<32, 1, 4>(g, s);              /* 32 channels per CTA row */
+    }
+    if (g.nch == 16) return launch_wide<16, 1, 1>(g, s);
+    if (g.nch % 64 == 0) return launch_wide<32, 2, 1>(g, s);
+    return launch_wide<32, 1, 1>(g, s);
+}
+
+} // namespace tronb

@@ -56,6 +56,8 @@ struct DegridLaunch {
 };
 
 int launch_grid(const GridLaunch &g, cudaStream_t s);
+bool grid_wide_applicable(const GridLaunch &g);
+int launch_grid_wide(const GridLaunch &g, cudaStream_t s);
 int launch_degrid(const DegridLaunch &d, cudaStream_t s);
 int launch_build_tables(SpokeTables &t, int npe, int npe_formula, int ntab, int tab_stride, int skip, int golden,
                         int adjoint, int win, int slide, int gs, int nslices, int n, float W, cudaStream_t s);
