@@ -36,11 +36,13 @@ struct __align__(16) WideList {
     int mask[WCAP];                   /* slices of the group whose window holds the spoke */
 };
 
+/* volatile: the drain loop relies on program order (all sample loads of a step, then the FMAs) --
+ * left to itself ptxas pairs each load with its first use and no load is ever in flight */
 __device__ __forceinline__ void ffma2w(float2 &acc, float w, float2 v)
 {
     unsigned long long a = *reinterpret_cast<unsigned long long *>(&acc);
     float2 ww = make_float2(w, w);
-    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;"
         : "+l"(a)
         : "l"(*reinterpret_cast<unsigned long long *>(&ww)), "l"(*reinterpret_cast<unsigned long long *>(&v)));
     acc = *reinterpret_cast<float2 *>(&a);
@@ -50,55 +52,61 @@ template <bool HALF>
 __device__ __forceinline__ float2 load_chan(const void *base, size_t idx)
 {
     if (HALF) {
-        unsigned raw = __ldg((const unsigned *)base + idx);
+        unsigned raw;
+        asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(raw) : "l"((const unsigned *)base + idx));
         return __half22float2(*reinterpret_cast<__half2 *>(&raw));
     }
-    return __ldg((const float2 *)base + idx);
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"((const float2 *)base + idx));
+    return v;
 }
 
-/* phase B: consume the list.  LPC = lanes per entry (32, or 16: two entries per iteration). */
+/* phase B: consume the list.  LPC = lanes per entry (32, or 16: two entries per step).
+ * The list is first padded to a whole number of steps with zero-weight copies of its last entry
+ * (same sample, so no new address is touched), which keeps the loop body free of branches;
+ * DEPTH steps are in flight: offsets first, then the sample loads, then the FMAs. */
 template <int LPC, int NCHUNK, int GS, bool HALF>
-__device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], const WideList &L, int cnt,
+__device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], WideList &L, int cnt,
                                            const void *samples, int lane, int nvalid)
 {
-    constexpr int EPI = 32 / LPC;                    /* entries per iteration */
-    const int sub = lane / LPC, ch = lane % LPC;
+    constexpr int EPI = 32 / LPC;                    /* entries per step */
+    constexpr int DEPTH = NCHUNK == 1 ? 8 : 4;
+    constexpr int STEP = DEPTH * EPI;
+    if (cnt == 0) return;
+    const int padded = ((cnt + STEP - 1) / STEP) * STEP;     /* <= WCAP: WCAP is a multiple of STEP */
+    if (cnt + lane < padded) {
+        L.wa[cnt + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        L.wb[cnt + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        L.off[cnt + lane] = L.off[cnt - 1];
+        L.mask[cnt + lane] = 0;
+    }
     __syncwarp();
-    for (int e0 = 0; e0 < cnt; e0 += 2 * EPI) {      /* two iterations in flight */
-        const int ea = e0 + sub, eb = e0 + EPI + sub;
-        const bool va = ea < cnt, vb = eb < cnt;
-        const int offa = va ? L.off[ea] : 0, offb = vb ? L.off[eb] : 0;
-        float2 xa[NCHUNK], xb[NCHUNK];
+    const int sub = lane / LPC;
+    const int ch = min(lane % LPC, nvalid - 1);      /* lanes past the last channel recompute it; never stored */
+    for (int e0 = 0; e0 < padded; e0 += STEP) {
+        float2 x[DEPTH][NCHUNK];
 #pragma unroll
-        for (int c = 0; c < NCHUNK; ++c) {
-            const bool cok = c * 32 + ch < nvalid;       /* channels beyond the plan's last one are not read */
-            xa[c] = va && cok ? load_chan<HALF>(samples, (size_t)offa + c * 32 + ch) : make_float2(0.f, 0.f);
-            xb[c] = vb && cok ? load_chan<HALF>(samples, (size_t)offb + c * 32 + ch) : make_float2(0.f, 0.f);
+        for (int d = 0; d < DEPTH; ++d) {
+            const int off = L.off[e0 + d * EPI + sub];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c)
+                x[d][c] = load_chan<HALF>(samples, (size_t)off + min(c * 32 + ch, nvalid - 1));
         }
-        if (va) {
-            const float4 p = L.wa[ea], q = L.wb[ea];
-            const int m = GS > 1 ? L.mask[ea] : 1;
-            const float w[8] = { p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            const int e = e0 + d * EPI + sub;
+            const float4 p = L.wa[e], q = L.wb[e];
+            const int m = GS > 1 ? L.mask[e] : 1;
 #pragma unroll
             for (int s = 0; s < GS; ++s)
                 if (GS == 1 || (m >> s) & 1) {
 #pragma unroll
-                    for (int c = 0; c < NCHUNK; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) ffma2w(acc[c][s][i], w[i], xa[c]);
-                }
-        }
-        if (vb) {
-            const float4 p = L.wa[eb], q = L.wb[eb];
-            const int m = GS > 1 ? L.mask[eb] : 1;
-            const float w[8] = { p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w };
-#pragma unroll
-            for (int s = 0; s < GS; ++s)
-                if (GS == 1 || (m >> s) & 1) {
-#pragma unroll
-                    for (int c = 0; c < NCHUNK; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) ffma2w(acc[c][s][i], w[i], xb[c]);
+                    for (int c = 0; c < NCHUNK; ++c) {
+                        ffma2w(acc[c][s][0], p.x, x[d][c]); ffma2w(acc[c][s][1], p.y, x[d][c]);
+                        ffma2w(acc[c][s][2], p.z, x[d][c]); ffma2w(acc[c][s][3], p.w, x[d][c]);
+                        ffma2w(acc[c][s][4], q.x, x[d][c]); ffma2w(acc[c][s][5], q.y, x[d][c]);
+                        ffma2w(acc[c][s][6], q.z, x[d][c]); ffma2w(acc[c][s][7], q.w, x[d][c]);
+                    }
                 }
         }
     }
@@ -184,7 +192,7 @@ grid_wide_kernel(const GridLaunch g)
             int cnt = 0;
 
             for (int it0 = 0; it0 < count; it0 += 32) {
-                /* phase A: lane = spoke */
+                /* phase A, step 1: lane = spoke of the window: its radii inside the block's support box */
                 const int it = it0 + lane;
                 const bool have = it < count;
                 int k = kstart + (have ? it : 0);
@@ -198,29 +206,47 @@ grid_wide_kernel(const GridLaunch g)
                 lo = fminf(fmaxf(lo, -Rmaxf), Rmaxf + 1.f); hi = fmaxf(fminf(hi, Rmaxf), -Rmaxf - 1.f);
                 const int r0 = (int)ceilf(lo);
                 int len = (int)floorf(hi) - r0 + 1;
-                if (!have || (GS > 1 && (pm >> 24) == 0)) len = 0;
-                const int maxlen = __reduce_max_sync(0xffffffffu, len);
-                const int spoke_off = (pm & 0xffffff) * g.nro + g.nro / 2;     /* sample index of ro = nro/2 */
-                for (int i = 0; i < maxlen; ++i) {
-                    const int r = r0 + i;
+                if (len < 0 || !have || (GS > 1 && (pm >> 24) == 0)) len = 0;
+                /* exclusive prefix of the lengths: candidate f of this batch belongs to the last lane with pre <= f */
+                int pre = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, pre, o);
+                    if (lane >= o) pre += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, pre, 31);
+                pre -= len;
+                /* step 2: lane = candidate (spoke, radius), flattened so that all lanes work */
+                for (int f0 = 0; f0 < total; f0 += 32) {
+                    const int f = f0 + lane;
+                    int own = 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const int cand = own + o;
+                        const int pc = __shfl_sync(0xffffffffu, pre, cand & 31);
+                        if (cand < 32 && pc <= f) own = cand;
+                    }
+                    const float ct = __shfl_sync(0xffffffffu, e.x, own), st = __shfl_sync(0xffffffffu, e.y, own);
+                    const int pmo = __shfl_sync(0xffffffffu, pm, own);
+                    const int r = __shfl_sync(0xffffffffu, r0, own) + (f - __shfl_sync(0xffffffffu, pre, own));
                     const float rf = (float)r;
                     const int ar = abs(r);
+                    const int ridx = same ? r : (r * g.nro) / g.n;                      /* tron.cu:517 */
                     float w8[8];
                     bool any = false;
-                    if (i < len) {
+                    if (f < total) {
                         float wx[4], wy[2];
 #pragma unroll
                         for (int cx = 0; cx < 4; ++cx) {
-                            const float dx = fma_ftz(e.x, rf, -(float)(X0 + cx));      /* tron.cu:514 as compiled */
+                            const float dx = fma_ftz(ct, rf, -(float)(X0 + cx));        /* tron.cu:514 as compiled */
                             wx[cx] = fabsf(dx) < W ? kb_weight(dx, g.kb) : 0.f;
                         }
-                        const int ridx = same ? r : (r * g.nro) / g.n;                  /* tron.cu:517 */
-                        float f = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);           /* tron.cu:412 */
-                        if (r == 0) f += f;                                              /* r = 0 visited twice */
+                        float fs = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);          /* tron.cu:412 */
+                        if (r == 0) fs += fs;                                            /* r = 0 visited twice */
 #pragma unroll
                         for (int cy = 0; cy < 2; ++cy) {
-                            const float dy = fma_ftz(e.y, rf, -(float)(Y0 + cy));
-                            wy[cy] = fabsf(dy) < W ? kb_weight(dy, g.kb) * f : 0.f;
+                            const float dy = fma_ftz(st, rf, -(float)(Y0 + cy));
+                            wy[cy] = fabsf(dy) < W ? kb_weight(dy, g.kb) * fs : 0.f;
                         }
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -233,11 +259,10 @@ grid_wide_kernel(const GridLaunch g)
                     const unsigned hit = __ballot_sync(0xffffffffu, any);
                     if (any) {
                         const int slot = cnt + __popc(hit & ((1u << lane) - 1u));
-                        const int ridx = same ? r : (r * g.nro) / g.n;
                         L.wa[slot] = make_float4(w8[0], w8[1], w8[2], w8[3]);
                         L.wb[slot] = make_float4(w8[4], w8[5], w8[6], w8[7]);
-                        L.off[slot] = (spoke_off + ridx) * g.nc_total;
-                        L.mask[slot] = pm >> 24;
+                        L.off[slot] = ((pmo & 0xffffff) * g.nro + g.nro / 2 + ridx) * g.nc_total;
+                        L.mask[slot] = pmo >> 24;
                     }
                     cnt += __popc(hit);
                     if (cnt + 32 > WCAP) {                       /* phase B: lanes = channels */
