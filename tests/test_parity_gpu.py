@@ -460,3 +460,29 @@ def test_wide_channel_fp16_storage(lib):
     with t.Plan(flags_to_cfg(dims, flags, half_in=True)) as p:
         got = p.recon_host(h16)
     assert rel_l2(got, want) <= TOL_F16
+
+
+@pytest.mark.parametrize("nc,flags", [
+    (32, dict(adjoint=False, golden=True)),
+    (32, dict(adjoint=False, undersamp=0.5, skip_angles=3)),                     # linear angles
+    (64, dict(adjoint=False, golden=True, kernwidth=6.0)),                       # cfg5 kernel width, 2 channels per lane
+    (32, dict(adjoint=False, golden=True, kernwidth=2.5, undersamp=0.3)),
+])
+def test_wide_channel_degridding_vs_reference(lib, reflib, nc, flags):
+    """Forward path with nc >= 32 (lanes = channels kernel) against the reference and the thread-per-sample kernel."""
+    import tron_b200 as t
+    torch_cuda()
+    dims = [nc, 1, 48, 48, 1]
+    h_in = synth_complex((int(np.prod(dims)),), stream=300 + nc)
+    want = run_ref(reflib, dims, flags, h_in)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        got = p.recon_host(h_in)
+    assert rel_l2(got, want) <= TOL_F32, rel_l2(got, want)
+    assert np.array_equal(got != 0, want != 0)
+    os.environ["TRON_NO_WIDE"] = "1"
+    try:
+        with t.Plan(flags_to_cfg(dims, flags)) as p:
+            other = p.recon_host(h_in)
+    finally:
+        del os.environ["TRON_NO_WIDE"]
+    assert rel_l2(got, other) <= 2e-6

@@ -59,9 +59,10 @@ degrid_gather_kernel(const DegridLaunch d)
 
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (size_t)gridDim.x * blockDim.x) {
-        /* chunk fastest so that a warp's stores to one sample are contiguous */
-        const int chunk = (int)(t % nchunk);
-        const size_t id = t / nchunk;
+        /* sample fastest: the lanes of a warp are consecutive samples of one spoke, so their taps fall
+         * on neighbouring cells of the same channel plane (chunk-fastest made every load touch 32 planes) */
+        const int chunk = (int)(t / nsamp);
+        const size_t id = t - (size_t)chunk * nsamp;
         const int pe = (int)(id / d.nro), ro = (int)(id - (size_t)pe * d.nro);
         const float2 cs = __ldg(d.cs + pe);
         const float R = fma_ftz((float)ro, inv_nro, -0.5f);

@@ -1,0 +1,201 @@
+/*
+ * degrid_wide.cu -- degridding for many receive channels (nc a multiple of 32): lanes = channels.
+ *
+ * Same operator and tap set as degrid.cu (reference: degridradial2d,
+ * /root/reference/src/tron.cu:540-577).  A warp owns four consecutive samples of one spoke; their
+ * tap windows overlap almost completely (neighbouring samples are one cell apart), so the warp
+ * walks the union window once:
+ *
+ *   A  lanes = rows / columns of the union window: the Kaiser-Bessel factor of every row and
+ *      every column for each of the four samples (zero outside that sample's own support, decided
+ *      by the reference predicate |xu - X| < W on the reference's coordinates, refmath.cuh);
+ *   B  lanes = channels: every grid cell of the union window is loaded once, as one coalesced
+ *      request from the channel-interleaved grid, and feeds the four samples' accumulators with
+ *      packed FFMA2s.
+ *
+ * With -k 6 (13 x 13 taps) this is FP32 bound; the point of the blocking is
+ * that a cell costs one load + four FMAs instead of four loads + four FMAs, all requests are full
+ * lines, and the per-tap weight work is amortised over the channels.
+ *
+ * Input grid: channel-interleaved g[(row*n + col)*nch + ch] (fwd FFT output transposed by
+ * planar_to_interleaved_kernel); output: samples[(pe*nro + ro)*nc_total + ch0 + ch].
+ */
+#include "tron_internal.h"
+
+namespace tronb {
+
+#define DW_S 4            /* samples per warp */
+#define DW_MAXU 20        /* union window side: floor(2W)+1 + DW_S-1 + slack <= 20  (W <= 7.5) */
+
+struct __align__(16) DwWeights {
+    float4 wx[DW_MAXU];   /* row factor of samples 0..3 */
+    float4 wy[DW_MAXU];   /* column factor */
+};
+
+__device__ __forceinline__ void ffma2d(float2 &acc, float w, float2 v)
+{
+    unsigned long long a = *reinterpret_cast<unsigned long long *>(&acc);
+    float2 ww = make_float2(w, w);
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;"
+                 : "+l"(a)
+                 : "l"(*reinterpret_cast<unsigned long long *>(&ww)), "l"(*reinterpret_cast<unsigned long long *>(&v)));
+    acc = *reinterpret_cast<float2 *>(&a);
+}
+
+__device__ __forceinline__ float2 ldg2v(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+template <int NCHUNK, bool HALF>
+__global__ void __launch_bounds__(256)
+degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interleaved grid */)
+{
+    __shared__ DwWeights sw[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DwWeights &S = sw[warp];
+    const int n = d.n, nch = d.nch;
+    const int groups_per_spoke = (d.nro + DW_S - 1) / DW_S;
+    const long long ngroups = (long long)groups_per_spoke * d.npe;
+    const float W = d.kb.W;
+    const float c0 = (float)((n + 1) / 2);
+    const float inv_nro = rcp_approx((float)d.nro);
+    const int chan0 = blockIdx.y * 32 * NCHUNK;
+
+    for (long long grp = (long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (long long)gridDim.x * 8) {
+        const int pe = (int)(grp / groups_per_spoke);
+        const int ro0 = (int)(grp - (long long)pe * groups_per_spoke) * DW_S;
+        const float2 cs = __ldg(d.cs + pe);
+        /* coordinates of the four samples, exactly as tron.cu:554-561 compiles */
+        float X[DW_S], Y[DW_S];
+        int xlo = 1 << 30, xhi = -(1 << 30), ylo = 1 << 30, yhi = -(1 << 30);
+#pragma unroll
+        for (int s = 0; s < DW_S; ++s) {
+            const float R = fma_ftz((float)(ro0 + s), inv_nro, -0.5f);
+            const float nR = mul_ftz(R, (float)n);
+            X[s] = fma_ftz(cs.y, nR, c0);            /* rows:    sin */
+            Y[s] = fma_ftz(cs.x, nR, c0);            /* columns: cos */
+            if (ro0 + s < d.nro) {
+                xlo = min(xlo, (int)ceilf(X[s] - W)); xhi = max(xhi, (int)floorf(X[s] + W));
+                ylo = min(ylo, (int)ceilf(Y[s] - W)); yhi = max(yhi, (int)floorf(Y[s] + W));
+            }
+        }
+        const int nux = min(xhi - xlo + 1, DW_MAXU), nuy = min(yhi - ylo + 1, DW_MAXU);
+
+        /* phase A: lanes 0..nux-1 rows, the others (offset 16 would not cover 20) -> two passes */
+        __syncwarp();
+        for (int i = lane; i < nux + nuy; i += 32) {
+            const bool isrow = i < nux;
+            const int u = isrow ? xlo + i : ylo + (i - nux);
+            float w4[DW_S];
+#pragma unroll
+            for (int s = 0; s < DW_S; ++s) {
+                const float dd = (float)u - (isrow ? X[s] : Y[s]);
+                const bool live = (ro0 + s < d.nro) && fabsf(dd) < W;     /* tron.cu:343 via gridkernel */
+                w4[s] = live ? kb_weight(dd, d.kb) : 0.f;
+            }
+            if (isrow) S.wx[i] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+            else S.wy[i - nux] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+        }
+        __syncwarp();
+
+        /* phase B: lanes = channels */
+        float2 acc[NCHUNK][DW_S];
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+            for (int s = 0; s < DW_S; ++s) acc[c][s] = make_float2(0.f, 0.f);
+        for (int i = 0; i < nux; ++i) {
+            const float4 a = S.wx[i];
+            const int row = (xlo + i + n) % n;                              /* periodic, tron.cu:569 */
+            const float2 *grow = gi + ((size_t)row * n) * nch + chan0 + lane;
+            for (int j0 = 0; j0 < nuy; j0 += 4) {
+                float2 v[4][NCHUNK];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int col = (ylo + min(j0 + jj, nuy - 1) + n) % n;
+#pragma unroll
+                    for (int c = 0; c < NCHUNK; ++c) v[jj][c] = ldg2v(grow + (size_t)col * nch + c * 32);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    if (j0 + jj < nuy) {
+                        const float4 b = S.wy[j0 + jj];
+                        const float w0 = a.x * b.x, w1 = a.y * b.y, w2 = a.z * b.z, w3 = a.w * b.w;
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c) {
+                            ffma2d(acc[c][0], w0, v[jj][c]); ffma2d(acc[c][1], w1, v[jj][c]);
+                            ffma2d(acc[c][2], w2, v[jj][c]); ffma2d(acc[c][3], w3, v[jj][c]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < DW_S; ++s) {
+            if (ro0 + s >= d.nro) continue;
+            const size_t base = ((size_t)pe * d.nro + ro0 + s) * d.nc_total + d.ch0 + chan0 + lane;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                if (chan0 + c * 32 + lane >= nch) continue;
+                if (HALF) ((__half2 *)d.samples)[base + c * 32] = __float22half2_rn(acc[c][s]);
+                else ((float2 *)d.samples)[base + c * 32] = acc[c][s];
+            }
+        }
+    }
+}
+
+/* planar [ch][cell] -> interleaved [cell][ch], 32 x 32 tiles through shared memory */
+__global__ void __launch_bounds__(256)
+planar_to_interleaved_kernel(float2 *__restrict__ dst, const float2 *__restrict__ src, int nch, size_t ncell)
+{
+    __shared__ float2 tile[32][33];
+    const size_t cell0 = (size_t)blockIdx.x * 32;
+    const int ch0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      /* 32 x 8 threads */
+    for (int r = ty; r < 32; r += 8) {
+        const int ch = ch0 + r;
+        const size_t cell = cell0 + tx;
+        tile[r][tx] = (ch < nch && cell < ncell) ? src[(size_t)ch * ncell + cell] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const size_t cell = cell0 + r;
+        const int ch = ch0 + tx;
+        if (ch < nch && cell < ncell) dst[cell * nch + ch] = tile[tx][r];
+    }
+}
+
+bool degrid_wide_applicable(const DegridLaunch &d)
+{
+    if (d.nch < 32 || d.nch % 32 != 0) return false;
+    if ((int)floorf(2.f * d.kb.W) + 1 + DW_S - 1 + 1 > DW_MAXU) return false;
+    return true;
+}
+
+/* scratch: nch*n*n float2, receives the channel-interleaved copy of the planar grid */
+int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
+{
+    const size_t ncell = (size_t)d.n * d.n;
+    dim3 tg((unsigned)((ncell + 31) / 32), (unsigned)((d.nch + 31) / 32));
+    planar_to_interleaved_kernel<<<tg, 256, 0, s>>>(scratch, d.grid, d.nch, ncell);
+    TRON_CUDA(cudaGetLastError());
+    const long long ngroups = (long long)((d.nro + DW_S - 1) / DW_S) * d.npe;
+    int bx = (int)((ngroups + 7) / 8);
+    if (bx > 148 * 32) bx = 148 * 32;
+    if (d.nch % 64 == 0) {
+        dim3 grid(bx, d.nch / 64);
+        if (d.half_out) degrid_wide_kernel<2, true><<<grid, 256, 0, s>>>(d, scratch);
+        else            degrid_wide_kernel<2, false><<<grid, 256, 0, s>>>(d, scratch);
+    } else {
+        dim3 grid(bx, d.nch / 32);
+        if (d.half_out) degrid_wide_kernel<1, true><<<grid, 256, 0, s>>>(d, scratch);
+        else            degrid_wide_kernel<1, false><<<grid, 256, 0, s>>>(d, scratch);
+    }
+    TRON_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // namespace tronb

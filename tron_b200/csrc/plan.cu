@@ -129,7 +129,7 @@ static void plan_release(tron_plan *p)
     cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
     fft_plan_free(p->fft);
     cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->heavy_cells); cudaFree(p->grid_dbg);
-    cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_in); cudaFree(p->d_out);
+    cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_gridi); cudaFree(p->d_in); cudaFree(p->d_out);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_in) cudaStreamDestroy(p->copy_in);
     if (p->copy_out) cudaStreamDestroy(p->copy_out);
@@ -245,6 +245,8 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     p->overlap = cfg->adjoint && p->nslices > p->batch && getenv("TRON_OVERLAP") != nullptr;   /* measured slower on B200: off */
     PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)(p->overlap ? 2 : 1) * p->batch * p->nch * n * n * sizeof(float2)));
     PLAN_CUDA(cudaMalloc(&p->d_tmp, (size_t)p->batch * p->nch * n * g.nx * sizeof(float2)));
+    if (!cfg->adjoint && p->nch >= 32 && p->nch % 32 == 0)
+        PLAN_CUDA(cudaMalloc(&p->d_gridi, (size_t)p->nch * n * n * sizeof(float2)));
     PLAN_CUDA(cudaStreamSynchronize(p->stream));
 #undef PLAN_TRY
 #undef PLAN_CUDA
@@ -395,6 +397,12 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     return TRON_OK;
 }
 
+static int run_degrid(tron_plan *p, const DegridLaunch &d, cudaStream_t s)
+{
+    if (p->d_gridi && degrid_wide_applicable(d) && !getenv("TRON_NO_WIDE")) return launch_degrid_wide(d, p->d_gridi, s);
+    return launch_degrid(d, s);
+}
+
 static int run_forward(tron_plan *p, void *d_out, const void *d_in, cudaStream_t s)
 {
     const tron_geometry &g = p->g;
@@ -408,7 +416,7 @@ static int run_forward(tron_plan *p, void *d_out, const void *d_in, cudaStream_t
     d.n = g.nxos; d.nro = g.nro; d.npe = g.npe1work;
     d.nc_total = g.nc * g.nt; d.ch0 = g.coil_begin; d.nch = p->nch;
     d.kb = p->kb; d.half_out = p->cfg.half_out;
-    rc = launch_degrid(d, s);
+    rc = run_degrid(p, d, s);
     p->last_launches += 3;
     return rc;
 }
@@ -476,7 +484,7 @@ extern "C" int tron_degrid_device(tron_plan *p, void *d_samples, const void *d_g
     d.n = g.nxos; d.nro = g.nro; d.npe = g.npe1work;
     d.nc_total = g.nc * g.nt; d.ch0 = 0; d.nch = p->nch;
     d.kb = p->kb; d.half_out = p->cfg.half_out;
-    return launch_degrid(d, s);
+    return run_degrid(p, d, s);
 }
 
 extern "C" int tron_plan_last_stage_ms(tron_plan *p, float ms[3])

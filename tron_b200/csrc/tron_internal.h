@@ -59,6 +59,8 @@ int launch_grid(const GridLaunch &g, cudaStream_t s);
 bool grid_wide_applicable(const GridLaunch &g);
 int launch_grid_wide(const GridLaunch &g, cudaStream_t s);
 int launch_degrid(const DegridLaunch &d, cudaStream_t s);
+bool degrid_wide_applicable(const DegridLaunch &d);
+int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s);
 int launch_build_tables(SpokeTables &t, int npe, int npe_formula, int ntab, int tab_stride, int skip, int golden,
                         int adjoint, int win, int slide, int gs, int nslices, int n, float W, cudaStream_t s);
 int build_tile_order(int **d_order, int n);
@@ -125,6 +127,7 @@ struct tron_plan {
     long long *grid_dbg = nullptr;       /* TRON_GRID_DEBUG: per-warp cycles of the last gridding launch */
     int nheavy = 0, heavy_r2 = -1;
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
+    float2 *d_gridi = nullptr;                      /* forward, nc >= 32: channel-interleaved copy of the grid */
     void *d_in = nullptr, *d_out = nullptr;         /* device staging for the host API */
     size_t in_bytes = 0, out_bytes = 0;
     size_t in_elem_bytes = 8, out_elem_bytes = 8;
