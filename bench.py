@@ -275,6 +275,77 @@ def run_ours(args):
     return out
 
 
+def run_cfg5(args):
+    """BASELINE cfg5: fp16-storage forward + adjoint NUFFT pair, 1024 matrix, 2x grid, kernel width 6,
+    64 coils sharded over the ranks; the coil root-sum-of-squares is one NCCL reduce of nx*ny floats.
+    Strong scaling: the 64 coils are split over the ranks (nc_local = 64 / N)."""
+    import torch
+    import tron_b200 as t
+    from tron_b200 import build
+    build.build()
+    rank, world, local = dist_setup(args.gpus)
+    nc, nx = 64, 1024
+    ncl = nc // world
+    fw = t.Plan(t.make_config([ncl, 1, nx, nx, 1], adjoint=False, kernwidth=6.0, half_in=True, half_out=True, device=local))
+    gf = fw.geom.as_dict()
+    ad = t.Plan(t.make_config([ncl, 1, gf["nro"], gf["npe1work"], 1], adjoint=True, kernwidth=6.0, half_in=True,
+                              sos_partial=(ncl > 1), device=local))
+    ga = ad.geom.as_dict()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(20261017 + 5 + 1000 * rank)
+    d_img = torch.randn(gf["in_elems"] * 2, device="cuda", generator=gen).to(torch.float16)
+    d_smp = torch.zeros(gf["out_elems"] * 2, device="cuda", dtype=torch.float16)
+    d_sos = torch.zeros(ga["nx"] * ga["ny"] * (1 if ncl > 1 else 2), device="cuda", dtype=torch.float32)
+    h_img = torch.empty(gf["in_elems"] * 2, dtype=torch.float16, pin_memory=True); h_img.copy_(d_img)
+    h_out = torch.empty(ga["nx"] * ga["ny"], dtype=torch.float32, pin_memory=True)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(from_host):
+        if from_host:
+            d_img.copy_(h_img, non_blocking=True)
+        fw.recon_device(d_smp.data_ptr(), d_img.data_ptr(), stream)
+        ad.recon_device(d_sos.data_ptr(), d_smp.data_ptr(), stream)
+        if world > 1:
+            import torch.distributed as dist
+            dist.reduce(d_sos, dst=0, op=dist.ReduceOp.SUM)          # the one collective of the coil-sharded path
+        img = torch.sqrt(d_sos) if ncl > 1 else d_sos
+        if from_host:
+            h_out.copy_(img[: h_out.numel()], non_blocking=True)
+        return img
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(False)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(True)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps, world)
+    nsamp = 2 * nc * gf["nro"] * gf["npe1work"]                     # forward + adjoint coil-samples
+    if rank == 0:
+        print(json.dumps({"metric": "radial k-space samples gridded/sec", "value": nsamp / (ms * 1e-3), "unit": "samples/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 storage)",
+                          "data": "synthetic",
+                          "config": {"workload": "BASELINE cfg5 fp16-storage forward+adjoint pair: 1024 matrix, 2x grid, "
+                                                 "kernel width 6, 64 coils coil-sharded, NCCL reduce of the partial sum of squares",
+                                     "name": "cfg5", "coils_per_gpu": ncl},
+                          "e2e": {"value": nsamp / e2e_s, "unit": "samples/s", "ms_per_step": e2e_s * 1e3,
+                                  "h2d_bytes_per_step": gf["in_elems"] * 4, "d2h_bytes_per_step": ga["nx"] * ga["ny"] * 4},
+                          "gpu_launches": (fw.last_launches() + ad.last_launches()) * args.steps}), flush=True)
+    fw.close(); ad.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(); dist.destroy_process_group()
+
+
 def run_reference(args):
     """The unmodified reference (CUDA + cuFFT) on the same GPU, through its own recon_radial2d."""
     rank = int(os.environ.get("RANK", "0"))
@@ -339,11 +410,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_cfg5(args)
     else:
         run_ours(args)
 

@@ -486,3 +486,29 @@ def test_wide_channel_degridding_vs_reference(lib, reflib, nc, flags):
     finally:
         del os.environ["TRON_NO_WIDE"]
     assert rel_l2(got, other) <= 2e-6
+
+
+def test_shepp_logan_round_trip(lib, reflib):
+    """BASELINE config 1: forward (RUNME1 flags = defaults) then adjoint on a 256^2 Shepp-Logan phantom,
+    both steps against the reference; the golden-angle pair (-G / -a -G) must give back the phantom."""
+    import tron_b200 as t
+    from util import shepp_logan
+    torch_cuda()
+    ph = shepp_logan(256)
+    dims = [1, 1, 256, 256, 1]
+    for golden in (False, True):
+        f = dict(adjoint=False, golden=golden)
+        want = run_ref(reflib, dims, f, ph.ravel())
+        with t.Plan(flags_to_cfg(dims, f)) as p:
+            data = p.recon_host(ph.ravel())
+            assert [int(x) for x in p.geom.out_dims] == [1, 1, 512, 512, 1]
+        assert rel_l2(data, want) <= TOL_F32
+        a = dict(adjoint=True, golden=golden)
+        want_img = run_ref(reflib, [1, 1, 512, 512, 1], a, want)
+        with t.Plan(flags_to_cfg([1, 1, 512, 512, 1], a)) as p:
+            img = p.recon_host(data)
+        assert rel_l2(img, want_img) <= 2e-5          # two chained operators
+        if golden:                                     # consistent pair (SURVEY F8): looks like the phantom
+            rec = np.abs(img.reshape(256, 256)); ref_ph = np.abs(ph)
+            c = np.corrcoef(rec.ravel(), ref_ph.ravel())[0, 1]
+            assert c > 0.95, c

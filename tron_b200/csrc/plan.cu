@@ -345,8 +345,19 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     const size_t grid_elems = (size_t)p->batch * p->nch * g.nxos * g.nxos;
     size_t spokes_up = 0;
     int i = 0;
-    for (int z0 = 0; z0 < p->nslices; z0 += p->batch, i ^= 1) {
-        const int nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
+    const int gs = p->tabs.gs > 0 ? p->tabs.gs : 1;
+    for (int z0 = 0, nb = 0; z0 < p->nslices; z0 += nb, i ^= 1) {
+        nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
+        if (host && p->batch >= 8 * gs) {
+            /* host mode ramps the batch size up at the start and down at the end, so that the first
+             * upload and the last download (which nothing overlaps) are short */
+            int ramp = p->batch;
+            if (z0 < p->batch) ramp = z0 == 0 ? p->batch / 8 : (z0 < p->batch / 2 ? p->batch / 4 : p->batch / 2);
+            const int rem = p->nslices - z0;
+            if (rem <= p->batch) ramp = rem > p->batch / 4 ? rem / 2 : rem;
+            ramp = ((ramp + gs - 1) / gs) * gs;
+            if (ramp >= gs && ramp < nb) nb = ramp;
+        }
         float2 *gridbuf = p->d_grid + (overlap ? (size_t)i * grid_elems : 0);
         if (host) {
             size_t need = (size_t)(z0 + nb - 1) * g.prof_slide + g.npe1work;
