@@ -237,7 +237,8 @@ def run_ours(args):
     tj = os.path.join(ROOT, "profiles", "grid_traffic.json")
     if os.path.isfile(tj):
         try:
-            traffic = json.load(open(tj)).get(args.workload)
+            per_slice = json.load(open(tj)).get(args.workload + "_bytes_per_slice")
+            traffic = per_slice * B if per_slice else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "grid_gather_kernel (tron_grid_device, %d slices/launch)" % B,
