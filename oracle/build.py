@@ -38,10 +38,14 @@ def _run(cmd, cwd=None):
 
 def build_oracle(force=False):
     srcs = [os.path.join(HERE, "tron_oracle.c"), os.path.join(HERE, "tron_oracle.h")]
-    if not force and _newer(ORACLE_SO, srcs):
+    if not force and os.path.exists(ORACLE_SO) and (_newer(ORACLE_SO, srcs) or shutil.which("gcc") is None):
         return ORACLE_SO
+    # -march=native: rebuilt on whichever host runs it (a copied tree has fresh mtimes, so the GPU box
+    # recompiles for its own CPU); written to a temporary name and renamed so a reader never sees half a file
+    tmp = ORACLE_SO + ".%d.tmp" % os.getpid()
     _run(["gcc", "-O3", "-march=native", "-fopenmp", "-fno-fast-math", "-ffp-contract=off",
-          "-std=gnu99", "-shared", "-fPIC", "-o", ORACLE_SO, srcs[0], "-lm"])
+          "-std=gnu99", "-shared", "-fPIC", "-o", tmp, srcs[0], "-lm"])
+    os.replace(tmp, ORACLE_SO)
     return ORACLE_SO
 
 

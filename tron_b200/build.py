@@ -44,7 +44,13 @@ def sources():
     return out
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, check_stale=False):
+    """Build the library and the CLI.  By default an existing library is used as is (tests, bench.py
+    and every rank of a torchrun launch call this; the snapshot on the GPU box has fresh mtimes, so a
+    staleness check there would rebuild -- concurrently on all ranks).  `force` / `check_stale`
+    (the `python -m tron_b200.build` entry) rebuild when sources are newer."""
+    if os.path.exists(LIB) and os.path.exists(EXE) and not force and not check_stale:
+        return LIB
     if shutil.which("nvcc") is None:
         if os.path.exists(LIB):
             return LIB
@@ -85,4 +91,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, check_stale=True))
