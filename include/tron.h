@@ -135,6 +135,8 @@ int  tron_degrid_device(tron_plan *plan, void *d_samples, const void *d_grid, vo
 int  tron_plan_last_stage_ms(tron_plan *plan, float ms[3]);
 /* number of kernel launches issued by the last tron_recon_* call */
 int  tron_plan_last_launches(const tron_plan *plan);
+/* diagnostic (plan created with TRON_GRID_DEBUG set): per-warp cycle counts of the last gridding launch */
+int  tron_plan_grid_debug(tron_plan *plan, long long *h_cycles, int nwarps);
 
 const char *tron_last_error(void);
 int  tron_version(void);

@@ -67,6 +67,7 @@ EXPORTED_SYMBOLS = [
     "tron_config_defaults", "tron_geometry_compute", "tron_plan_create", "tron_plan_destroy",
     "tron_plan_geometry", "tron_recon_host", "tron_recon_device", "tron_grid_device",
     "tron_grid_to_interleaved", "tron_degrid_device", "tron_plan_last_stage_ms", "tron_plan_last_launches",
+    "tron_plan_grid_debug",
     "tron_last_error", "tron_version",
     # tron.h: legacy surface
     "tron_set_config", "tron_init", "tron_shutdown", "tron_nufft_adj_radial2d", "tron_nufft_radial2d",
