@@ -67,7 +67,7 @@ __device__ __forceinline__ int angle_bin(float a, float lut_scale, int nbins)
  * Entry k of a table: (cos, sin, 1/cos, 1/sin) of the k-th spoke by angle mod pi,
  * pe_sorted[k] = index of that spoke relative to the group's first spoke, with
  * bits 24.. = mask of the group's slices whose window [s*slide, s*slide+win) holds it. */
-__global__ void spoke_table_kernel(float4 *cs, int *pe_sorted, int *lut, float2 *cs_lin,
+__global__ void spoke_table_kernel(float4 *cs, int *pe_sorted, float4 *gx, int *lut, float2 *cs_lin,
                                    float *key_unsorted, float *key_sorted,
                                    int npe, int npe_formula, int tab_stride, int skip, int golden, int adjoint,
                                    int nbins, int win, int slide, int gs, int nslices)
@@ -89,6 +89,7 @@ __global__ void spoke_table_kernel(float4 *cs, int *pe_sorted, int *lut, float2 
     if (!adjoint) return;
     float4 *csd = cs + (size_t)tab * npe;
     int *ped = pe_sorted + (size_t)tab * npe;
+    float4 *gxd = gx + (size_t)tab * 2 * npe;             /* stored twice: a circular window never wraps */
     for (int pe = threadIdx.x; pe < npe; pe += blockDim.x) {
         float key = ku[pe];
         int rank = 0;
@@ -104,6 +105,7 @@ __global__ void spoke_table_kernel(float4 *cs, int *pe_sorted, int *lut, float2 
             if (tab * gs + s < nslices && pe >= s * slide && pe < s * slide + win) mask |= 1 << s;
         csd[rank] = make_float4(c.x, c.y, ic, is);
         ped[rank] = pe | (mask << 24);
+        gxd[rank] = gxd[rank + npe] = make_float4(c.x, c.y, __int_as_float(pe), __int_as_float(mask));
         ks[rank] = key;
     }
     __syncthreads();
@@ -149,20 +151,20 @@ __global__ void cell_table_kernel(int2 *cells, int n, float W, int nbins)
     }
 }
 
-/* tiles of 16x16 cells ordered by the distance of their nearest cell from DC */
-int build_tile_order(int **d_order, int n)
+/* tiles of 16 x th cells (one thread block each) ordered by the distance of their nearest cell from DC */
+int build_tile_order(int **d_order, int n, int th)
 {
-    int tx = (n + 15) / 16, nt = tx * tx;
+    int tx = (n + 15) / 16, nt = tx * ((n + th - 1) / th);
     std::vector<std::pair<float, int>> key(nt);
     for (int t = 0; t < nt; ++t) {
-        int x0 = (t % tx) * 16 - n / 2, y0 = (t / tx) * 16 - n / 2;
+        int x0 = (t % tx) * 16 - n / 2, y0 = (t / tx) * th - n / 2;
         float dx = x0 > 0 ? (float)x0 : (x0 + 15 < 0 ? (float)-(x0 + 15) : 0.f);
-        float dy = y0 > 0 ? (float)y0 : (y0 + 15 < 0 ? (float)-(y0 + 15) : 0.f);
+        float dy = y0 > 0 ? (float)y0 : (y0 + th - 1 < 0 ? (float)-(y0 + th - 1) : 0.f);
         key[t] = std::make_pair(dx * dx + dy * dy, t);
     }
     std::sort(key.begin(), key.end());
     std::vector<int> order(nt);
-    for (int t = 0; t < nt; ++t) order[t] = key[t].second;
+    for (int t = 0; t < nt; ++t) order[t] = ((key[t].second / tx) << 16) | (key[t].second % tx);   /* ty << 16 | tx */
     TRON_CUDA(cudaMalloc(d_order, nt * sizeof(int)));
     TRON_CUDA(cudaMemcpy(*d_order, order.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
     return 0;
@@ -217,6 +219,7 @@ int launch_build_tables(SpokeTables &t, int npe, int npe_formula, int ntab, int 
     if (adjoint) {
         TRON_CUDA(cudaMalloc(&t.cs, ne * sizeof(float4)));
         TRON_CUDA(cudaMalloc(&t.pe, ne * sizeof(int)));
+        TRON_CUDA(cudaMalloc(&t.gx, 2 * ne * sizeof(float4)));
         TRON_CUDA(cudaMalloc(&t.lut, (size_t)ntab * (t.nbins + 1) * sizeof(int)));
         TRON_CUDA(cudaMalloc(&t.cells, (size_t)n * n * sizeof(int2)));
         int blocks = (n * n + 255) / 256; if (blocks > 4096) blocks = 4096;
@@ -225,7 +228,7 @@ int launch_build_tables(SpokeTables &t, int npe, int npe_formula, int ntab, int 
     }
     TRON_CUDA(cudaMalloc(&scratch, 2 * ne * sizeof(float)));
     int threads = npe >= 1024 ? 1024 : 256;
-    spoke_table_kernel<<<ntab, threads, 0, s>>>(t.cs, t.pe, t.lut, t.cs_lin, scratch, scratch + ne,
+    spoke_table_kernel<<<ntab, threads, 0, s>>>(t.cs, t.pe, t.gx, t.lut, t.cs_lin, scratch, scratch + ne,
                                                 npe, npe_formula, tab_stride, skip, golden, adjoint, t.nbins,
                                                 win, slide, gs, nslices);
     TRON_CUDA(cudaGetLastError());
@@ -305,42 +308,42 @@ __device__ __forceinline__ void cell_setup(const GridLaunch &g, const int *__res
     if (c.Rlo > c.Rhi) c.count = 0;
 }
 
-/* Visit sorted-table entries kstart + first, kstart + first + step, ... (< count, circular). */
-template <int CH, int GS, bool HALF>
+/* Visit sorted-table entries kstart + first, kstart + first + step, ... (< count; the table is stored
+ * twice, so the circular window is a plain range).  `samples` points at sample ro = 0 of the group's
+ * first spoke (this thread's channel chunk).  The accumulators receive the final value: the output
+ * scale 1/(nxos*npe) (tron.cu:532) rides on the density compensation factor.
+ * PLAIN: the fitted Kaiser-Bessel polynomial is in use and nro == nxos (ridx = r) -- the usual case,
+ * compiled without the run-time alternatives. */
+template <int CH, int GS, bool HALF, bool PLAIN>
 __device__ __forceinline__ void gather_cell(float2 (&acc)[GS][CH], const GridLaunch &g,
-                                            const float4 *__restrict__ tab, const int *__restrict__ tpe,
-                                            const char *samples, const CellGeom &c, int first, int step)
+                                            const float4 *__restrict__ tab, const char *samples,
+                                            const CellGeom &c, int first, int step)
 {
     const float W = g.kb.W;
     const float Xf = (float)c.X, Yf = (float)c.Y, Rhif = (float)c.Rhi;
-    const float xm = Xf - W, xp = Xf + W, ym = Yf - W, yp = Yf + W;
-    const bool same = g.nro == g.n;                       /* ridx = r (gridos 2) */
-    const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
-    const size_t spoke_bytes = (size_t)g.nro * g.nc_total * esz;
-    const int samp_bytes = g.nc_total * (int)esz;
-    const char *centre = samples + (size_t)(g.nro / 2) * samp_bytes;
+    const bool same = PLAIN || g.nro == g.n;              /* ridx = r (gridos 2) */
+    const unsigned samp_bytes = (unsigned)g.nc_total * (unsigned)(HALF ? sizeof(__half2) : sizeof(float2));
+    const int half_nro = g.nro >> 1;
     /* the table entry of the next spoke is fetched while the current one is processed */
-    int k = c.kstart + first;
-    if (k >= g.npe) k -= g.npe;
-    float4 e = first < c.count ? __ldg(tab + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    int pm = first < c.count ? __ldg(tpe + k) : 0;
-    for (int it = first; it < c.count; it += step) {
-        const float4 ec = e;                              /* ct, st, 1/ct, 1/st */
-        const int pmc = pm;
-        if (it + step < c.count) {
-            k += step;
-            if (k >= g.npe) k -= g.npe;
-            e = __ldg(tab + k); pm = __ldg(tpe + k);
-        }
-        float ax = xm * ec.z, bx = xp * ec.z, ay = ym * ec.w, by = yp * ec.w;
+    const float4 *tp = tab + c.kstart + first;
+    float4 e = first < c.count ? __ldg(tp) : make_float4(1.f, 1.f, 0.f, 0.f);
+    for (int left = c.count - first; left > 0; left -= step) {
+        const float4 ec = e;                              /* ct, st, spoke index, slice mask */
+        tp += step;
+        if (left > step) e = __ldg(tp);
+        /* candidate radii: integer points of {|r ct - X| < W} n {|r st - Y| < W} with a margin; a zero
+         * cosine/sine gives +-inf bounds (or NaN when the cell cannot be reached: no candidates) */
+        const float icx = rcp_approx(ec.x), icy = rcp_approx(ec.y);
+        float ax = (Xf - W) * icx, bx = (Xf + W) * icx, ay = (Yf - W) * icy, by = (Yf + W) * icy;
         float lo = fmaxf(fminf(ax, bx), fminf(ay, by)) - 1e-3f;
         float hi = fminf(fmaxf(ax, bx), fmaxf(ay, by)) + 1e-3f;
         lo = fmaxf(lo, -Rhif); hi = fminf(hi, Rhif);
+        if (!(lo <= hi)) continue;
         int r0 = (int)ceilf(lo), r1 = (int)floorf(hi);
         if (r0 > r1) continue;
-        const int mask = GS > 1 ? (pmc >> 24) : 1;
+        const int mask = GS > 1 ? __float_as_int(ec.w) : 1;
         if (GS > 1 && mask == 0) continue;               /* spoke outside every window of a partial group */
-        const char *spoke = centre + (size_t)(pmc & 0xffffff) * spoke_bytes;  /* sample ro = nro/2 of this spoke */
+        const int centre = __float_as_int(ec.z) * g.nro + half_nro;       /* sample ro = nro/2 of this spoke */
         for (int r = r0; r <= r1; ++r) {
             if (abs(r) < c.Rlo) continue;                /* annulus, tron.cu:501-502,512,521 */
             float rf = (float)r;
@@ -351,9 +354,9 @@ __device__ __forceinline__ void gather_cell(float2 (&acc)[GS][CH], const GridLau
             /* the tap is live: start the sample load, evaluate the weight while it is in flight */
             int ridx = same ? r : (r * g.nro) / g.n;     /* tron.cu:517 */
             float2 v[CH];
-            load_sample<CH, HALF>(v, spoke + (ptrdiff_t)ridx * samp_bytes);
-            float w = kb_weight(dx, g.kb) * kb_weight(dy, g.kb);
-            float sdc = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);          /* tron.cu:412 */
+            load_sample<CH, HALF>(v, samples + (size_t)(unsigned)(centre + ridx) * samp_bytes);
+            float w = PLAIN ? kb_poly_xy(dx, dy, g.kb) : kb_weight_xy(dx, dy, g.kb);
+            float sdc = fmaf(g.sdc_as, fabsf((float)ridx), g.sdc_bs);        /* tron.cu:412, times the scale */
             w *= (r == 0) ? sdc + sdc : sdc;             /* both loops visit r = 0 */
             if (!(w > 0.f)) continue;                    /* the reference's wgt > 0 guard */
 #pragma unroll
@@ -367,14 +370,14 @@ __device__ __forceinline__ void gather_cell(float2 (&acc)[GS][CH], const GridLau
     }
 }
 
+/* blockIdx.x = slice group (fastest, so the groups of one tile run together), .y = tile rank, .z = chunk */
 template <int CH, int GS, bool HALF>
 __device__ __forceinline__ void group_pointers(const GridLaunch &g, int grp, int chunk, const float4 *&tab,
-                                               const int *&tpe, const int *&lut, const char *&samples)
+                                               const int *&lut, const char *&samples)
 {
     const int ug = g.z0 / GS + grp;                       /* slice group, shard-local */
     const int tabi = g.tab_per_slice ? ug : 0;
-    tab = g.tab_cs + (size_t)tabi * g.npe;
-    tpe = g.tab_pe + (size_t)tabi * g.npe;
+    tab = g.tab_gx + (size_t)tabi * 2 * g.npe;
     lut = g.lut + (size_t)tabi * (g.nbins + 1);
     const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
     samples = (const char *)g.samples
@@ -386,35 +389,33 @@ __device__ __forceinline__ void store_cell(const GridLaunch &g, const float2 (&a
                                            int x, int y)
 {
     const size_t plane = (size_t)g.n * g.n;
-    const int zg = (g.z0 / GS + grp) * GS;
+    const int zl0 = (g.z0 / GS + grp) * GS - g.z0;          /* slice index inside this launch of the group's first */
+    float2 *out = g.grid + ((ptrdiff_t)zl0 * g.nch + (ptrdiff_t)chunk * CH) * (ptrdiff_t)plane + (size_t)y * g.n + x;
+    const size_t slice_stride = (size_t)g.nch * plane;
 #pragma unroll
     for (int s = 0; s < GS; ++s) {
-        const int zl = zg + s - g.z0;                      /* slice index inside this launch */
-        if (zl < 0 || zl >= g.nslices) continue;
-        float2 *out = g.grid + ((size_t)zl * g.nch + (size_t)chunk * CH) * plane + (size_t)y * g.n + x;
+        if (zl0 + s >= 0 && zl0 + s < g.nslices) {
+            float2 *o = out;
 #pragma unroll
-        for (int i = 0; i < CH; ++i)
-            out[(size_t)i * plane] = make_float2(acc[s][i].x * g.scale, acc[s][i].y * g.scale);
+            for (int i = 0; i < CH; ++i) { *o = acc[s][i]; o += plane; }
+        }
+        out += slice_stride;
     }
 }
 
 /* main path: one thread per cell; cells inside the heavy disc are left to the heavy path */
-template <int CH, int GS, bool HALF>
-__device__ __forceinline__ void grid_tile_path(const GridLaunch &g, int block)
+template <int CH, int GS, bool HALF, int BT, bool PLAIN>
+__device__ __forceinline__ void grid_tile_path(const GridLaunch &g, int rank, int grp, int chunk)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = g.n;
-    const int tiles_x = (n + 15) >> 4;
-    const int rank = block / g.ngroups, grp = block - rank * g.ngroups;
-    const int tile = __ldg(g.tile_order + rank);
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int x = tx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = ty * 16 + (warp >> 1) * 4 + (lane >> 3);
-    const int chunk = blockIdx.y;
+    const int tile = __ldg((BT == 128 ? g.tile_order8 : g.tile_order) + rank);      /* ty << 16 | tx */
+    const int x = (tile & 0xffff) * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = (tile >> 16) * (BT / 16) + (warp >> 1) * 4 + (lane >> 3);
     if (x >= n || y >= n) return;
 
-    const float4 *tab; const int *tpe, *lut; const char *samples;
-    group_pointers<CH, GS, HALF>(g, grp, chunk, tab, tpe, lut, samples);
+    const float4 *tab; const int *lut; const char *samples;
+    group_pointers<CH, GS, HALF>(g, grp, chunk, tab, lut, samples);
     CellGeom c;
     cell_setup(g, lut, x, y, c);
     if (c.X * c.X + c.Y * c.Y <= g.heavy_r2) return;      /* integer test: identical on host and device */
@@ -424,24 +425,22 @@ __device__ __forceinline__ void grid_tile_path(const GridLaunch &g, int block)
     for (int s = 0; s < GS; ++s)
 #pragma unroll
         for (int i = 0; i < CH; ++i) acc[s][i] = make_float2(0.f, 0.f);
-    gather_cell<CH, GS, HALF>(acc, g, tab, tpe, samples, c, 0, 1);
+    gather_cell<CH, GS, HALF, PLAIN>(acc, g, tab, samples, c, 0, 1);
     store_cell<CH, GS>(g, acc, grp, chunk, x, y);
 }
 
 /* heavy path: one warp per cell, lanes stride over the spokes, shuffle reduction */
-template <int CH, int GS, bool HALF>
-__device__ __forceinline__ void grid_heavy_path(const GridLaunch &g, int block)
+template <int CH, int GS, bool HALF, int BT, bool PLAIN>
+__device__ __forceinline__ void grid_heavy_path(const GridLaunch &g, int hg, int grp, int chunk)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int hg = block / g.ngroups, grp = block - hg * g.ngroups;
-    const int ci = hg * 8 + warp;
-    const int chunk = blockIdx.y;
+    const int ci = hg * (BT / 32) + warp;
     if (ci >= g.nheavy) return;
     const int packed = __ldg(g.heavy_cells + ci);
     const int x = packed & 0xffff, y = packed >> 16;
 
-    const float4 *tab; const int *tpe, *lut; const char *samples;
-    group_pointers<CH, GS, HALF>(g, grp, chunk, tab, tpe, lut, samples);
+    const float4 *tab; const int *lut; const char *samples;
+    group_pointers<CH, GS, HALF>(g, grp, chunk, tab, lut, samples);
     CellGeom c;
     cell_setup(g, lut, x, y, c);
     float2 acc[GS][CH];
@@ -449,7 +448,7 @@ __device__ __forceinline__ void grid_heavy_path(const GridLaunch &g, int block)
     for (int s = 0; s < GS; ++s)
 #pragma unroll
         for (int i = 0; i < CH; ++i) acc[s][i] = make_float2(0.f, 0.f);
-    gather_cell<CH, GS, HALF>(acc, g, tab, tpe, samples, c, lane, 32);
+    gather_cell<CH, GS, HALF, PLAIN>(acc, g, tab, samples, c, lane, 32);
 #pragma unroll
     for (int s = 0; s < GS; ++s)
 #pragma unroll
@@ -463,32 +462,49 @@ __device__ __forceinline__ void grid_heavy_path(const GridLaunch &g, int block)
     if (lane == 0) store_cell<CH, GS>(g, acc, grp, chunk, x, y);
 }
 
-/* one launch: the heavy-cell blocks come first (longest critical path), then the tiles */
-template <int CH, int GS, bool HALF>
-__global__ void __launch_bounds__(256, (CH * GS >= 16 ? 3 : 4))
-grid_gather_kernel(const GridLaunch g)
+/* one launch: the heavy-cell blocks come first (longest critical path), then the tiles.
+ * Grid: x = slice group, y = heavy block / tile rank, z = channel chunk (launch_grid_cg).
+ * BT threads per block: 256 (16x16 tile), or 128 (16x8 tile) where the accumulators need the
+ * registers: 5 blocks of 128 threads leave 96 registers per thread, 3 of 256 only 80. */
+template <int CH, int GS, bool HALF, int BT, bool PLAIN>
+__global__ void __launch_bounds__(BT, (BT == 128 ? 5 : 4))
+grid_gather_kernel(const GridLaunch g, const int rank0)
 {
-    const int heavy_blocks = ((g.nheavy + 7) >> 3) * g.ngroups;
+    constexpr int WARPS = BT / 32;
+    const int heavy_blocks = (g.nheavy + WARPS - 1) / WARPS;
+    const int rank = rank0 + (int)blockIdx.y, grp = blockIdx.x, chunk = blockIdx.z;
     const long long t0 = g.dbg ? clock64() : 0;
-    if ((int)blockIdx.x < heavy_blocks) grid_heavy_path<CH, GS, HALF>(g, blockIdx.x);
-    else grid_tile_path<CH, GS, HALF>(g, blockIdx.x - heavy_blocks);
+    if (rank < heavy_blocks) grid_heavy_path<CH, GS, HALF, BT, PLAIN>(g, rank, grp, chunk);
+    else grid_tile_path<CH, GS, HALF, BT, PLAIN>(g, rank - heavy_blocks, grp, chunk);
     if (g.dbg) {                                          /* per-warp cycle counts (TRON_GRID_DEBUG) */
         __syncwarp();
         const long long t1 = clock64();
-        if ((threadIdx.x & 31) == 0) g.dbg[(size_t)blockIdx.x * 8 + (threadIdx.x >> 5)] = t1 - t0;
+        const size_t b = ((size_t)chunk * (gridDim.y + rank0) + rank) * gridDim.x + grp;
+        if ((threadIdx.x & 31) == 0 && b < (size_t)8 * 65536) g.dbg[b * 8 + (threadIdx.x >> 5)] = t1 - t0;
     }
+}
+
+template <int CH, int GS, bool HALF, bool PLAIN>
+static int launch_grid_cghp(const GridLaunch &g, cudaStream_t s)
+{
+    constexpr int BT = CH * GS >= 16 ? 128 : 256;
+    const int tiles = ((g.n + 15) / 16) * ((g.n + BT / 16 - 1) / (BT / 16));
+    const int ranks = tiles + (g.nheavy + BT / 32 - 1) / (BT / 32);
+    for (int r0 = 0; r0 < ranks; r0 += 65535) {            /* gridDim.y limit */
+        dim3 grid(g.ngroups, std::min(65535, ranks - r0), g.nch / CH);
+        grid_gather_kernel<CH, GS, HALF, BT, PLAIN><<<grid, BT, 0, s>>>(g, r0);
+        TRON_CUDA(cudaGetLastError());
+    }
+    return 0;
 }
 
 template <int CH, int GS>
 static int launch_grid_cg(GridLaunch g, cudaStream_t s)
 {
-    int tiles = ((g.n + 15) / 16) * ((g.n + 15) / 16);
     g.ngroups = (g.z0 + g.nslices - 1) / GS - g.z0 / GS + 1;
-    dim3 grid((tiles + (g.nheavy + 7) / 8) * g.ngroups, g.nch / CH);
-    if (g.half_in) grid_gather_kernel<CH, GS, true><<<grid, 256, 0, s>>>(g);
-    else           grid_gather_kernel<CH, GS, false><<<grid, 256, 0, s>>>(g);
-    TRON_CUDA(cudaGetLastError());
-    return 0;
+    const bool plain = g.kb.fast && g.nro == g.n;
+    if (g.half_in) return plain ? launch_grid_cghp<CH, GS, true, true>(g, s) : launch_grid_cghp<CH, GS, true, false>(g, s);
+    return plain ? launch_grid_cghp<CH, GS, false, true>(g, s) : launch_grid_cghp<CH, GS, false, false>(g, s);
 }
 
 int launch_grid(const GridLaunch &g, cudaStream_t s)

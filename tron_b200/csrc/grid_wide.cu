@@ -124,7 +124,7 @@ grid_wide_kernel(const GridLaunch g)
     const int tiles_x = (n + 15) >> 4;
     const int rank = blockIdx.x / g.ngroups, grp = blockIdx.x - rank * g.ngroups;
     const int tile = __ldg(g.tile_order + rank);
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int ty = tile >> 16, tx = tile & 0xffff;
     const int chan0 = blockIdx.y * (LPC * NCHUNK);           /* first plan-local channel of this CTA */
 
     const int ug = g.z0 / GS + grp;

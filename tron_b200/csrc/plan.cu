@@ -126,9 +126,9 @@ extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
 static void plan_release(tron_plan *p)
 {
     if (!p) return;
-    cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
+    cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.gx); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
     fft_plan_free(p->fft);
-    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->heavy_cells); cudaFree(p->grid_dbg);
+    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->heavy_cells); cudaFree(p->grid_dbg);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_gridi); cudaFree(p->d_in); cudaFree(p->d_out);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_in) cudaStreamDestroy(p->copy_in);
@@ -226,7 +226,8 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     }
     PLAN_TRY(fft_plan_init(p->fft, n, g.nx));
     if (cfg->adjoint) {
-        PLAN_TRY(build_tile_order(&p->tile_order, n));
+        PLAN_TRY(build_tile_order(&p->tile_order, n, 16));
+        PLAN_TRY(build_tile_order(&p->tile_order8, n, 8));
         PLAN_TRY(build_heavy_cells(&p->heavy_cells, &p->nheavy, &p->heavy_r2, n, p->tabs.npe, cfg->kernwidth));
     }
     PLAN_CUDA(cudaMalloc(&p->deapod_adj, (size_t)g.nx * g.nx * sizeof(float)));
@@ -275,8 +276,8 @@ static GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, fl
     const tron_geometry &g = p->g;
     GridLaunch L;
     L.samples = d_samples; L.grid = d_grid;
-    L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.lut = p->tabs.lut; L.cells = p->tabs.cells;
-    L.tile_order = p->tile_order;
+    L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.tab_gx = p->tabs.gx; L.lut = p->tabs.lut; L.cells = p->tabs.cells;
+    L.tile_order = p->tile_order; L.tile_order8 = p->tile_order8;
     L.heavy_cells = p->heavy_cells; L.nheavy = p->nheavy; L.heavy_r2 = p->heavy_r2;
     L.tab_per_slice = p->tabs.ntab > 1 ? 1 : 0;
     L.nbins = p->tabs.nbins;
@@ -288,6 +289,7 @@ static GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, fl
     L.sdc_a = (2.f - 2.f / (float)g.npe1work) / (float)g.nro;
     L.sdc_b = 1.f / (float)g.npe1work;
     L.scale = 1.f / (float)g.nxos / (float)g.npe1work;
+    L.sdc_as = L.sdc_a * L.scale; L.sdc_bs = L.sdc_b * L.scale;
     L.half_in = p->cfg.half_in;
     L.dbg = p->grid_dbg;
     return L;

@@ -20,6 +20,8 @@ int  cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 struct SpokeTables {
     float4 *cs = nullptr;     /* [ntab][npe]  (cos, sin, 1/cos, 1/sin), sorted by angle mod pi */
     int    *pe = nullptr;     /* [ntab][npe]  group-relative spoke index | slice mask << 24 */
+    float4 *gx = nullptr;     /* [ntab][2*npe] (cos, sin, bits: group-relative spoke index, bits: slice mask), same order,
+                                 stored twice back to back so a circular window is a plain range */
     int    *lut = nullptr;    /* [ntab][nbins+1] first sorted entry of each angular bin */
     float2 *cs_lin = nullptr; /* [ntab][npe]  (cos, sin) in acquisition order (degridding) */
     int2   *cells = nullptr;  /* [n][n] slice-independent cell geometry (band, angular bins) */
@@ -31,8 +33,9 @@ struct SpokeTables {
 struct GridLaunch {               /* everything the gridding kernel needs */
     const void *samples;          /* first spoke of shard-local slice 0 */
     float2 *grid;                 /* [nslices][nch][n][n] */
-    const float4 *tab_cs; const int *tab_pe; const int *lut; const int2 *cells;
-    const int *tile_order;        /* [tiles] heaviest (nearest DC) first */
+    const float4 *tab_cs; const int *tab_pe; const float4 *tab_gx; const int *lut; const int2 *cells;
+    const int *tile_order;        /* [tiles] 16x16 tiles, heaviest (nearest DC) first */
+    const int *tile_order8;       /* same for 16x8 tiles (128-thread blocks) */
     const int *heavy_cells; int nheavy; int heavy_r2;   /* cells with X^2+Y^2 <= heavy_r2: one warp each */
     int tab_per_slice;            /* 1: table index = slice group, 0: shared */
     int nbins;
@@ -42,6 +45,7 @@ struct GridLaunch {               /* everything the gridding kernel needs */
     int z0, nslices, slide;
     KbParams kb;
     float sdc_a, sdc_b, scale;
+    float sdc_as, sdc_bs;         /* sdc_a * scale, sdc_b * scale: the gather folds the output scale into the weight */
     int half_in;
     long long *dbg;               /* optional per-warp cycle counts [blocks][8] */
 };
@@ -63,7 +67,7 @@ bool degrid_wide_applicable(const DegridLaunch &d);
 int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s);
 int launch_build_tables(SpokeTables &t, int npe, int npe_formula, int ntab, int tab_stride, int skip, int golden,
                         int adjoint, int win, int slide, int gs, int nslices, int n, float W, cudaStream_t s);
-int build_tile_order(int **d_order, int n);
+int build_tile_order(int **d_order, int n, int th);
 int build_heavy_cells(int **d_cells, int *nheavy, int *heavy_r2, int n, int npe, float W);
 int launch_interleave(float2 *dst, const float2 *planar, int nch, int n, int nslices, cudaStream_t s);
 int launch_deinterleave(float2 *planar, const float2 *src, int nch, int n, cudaStream_t s);
@@ -123,7 +127,7 @@ struct tron_plan {
     tronb::SpokeTables tabs;
     tronb::FftPlan fft;
     float *deapod_adj = nullptr, *deapod_fwd = nullptr;
-    int *tile_order = nullptr, *heavy_cells = nullptr;
+    int *tile_order = nullptr, *tile_order8 = nullptr, *heavy_cells = nullptr;
     long long *grid_dbg = nullptr;       /* TRON_GRID_DEBUG: per-warp cycles of the last gridding launch */
     int nheavy = 0, heavy_r2 = -1;
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
