@@ -252,7 +252,34 @@ __device__ __forceinline__ void ffma2(float2 &acc, float w, float2 v)
     acc = *reinterpret_cast<float2 *>(&a);
 }
 
-/* CH channels of one sample (contiguous, channel fastest); fp16 storage converts on load */
+/* CH channels of one sample (contiguous, channel fastest); fp16 storage converts on load.
+ * The loads are volatile asm so that they stay where the source puts them -- ahead of the weight
+ * evaluation -- instead of being sunk below the last branch that could still drop the tap. */
+__device__ __forceinline__ float4 ldg_nc_f4(const void *p)
+{
+    float4 q;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(p));
+    return q;
+}
+__device__ __forceinline__ float2 ldg_nc_f2(const void *p)
+{
+    float2 q;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(q.x), "=f"(q.y) : "l"(p));
+    return q;
+}
+__device__ __forceinline__ uint2 ldg_nc_u2(const void *p)
+{
+    uint2 q;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(q.x), "=r"(q.y) : "l"(p));
+    return q;
+}
+__device__ __forceinline__ unsigned ldg_nc_u1(const void *p)
+{
+    unsigned q;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(q) : "l"(p));
+    return q;
+}
+
 template <int CH, bool HALF>
 __device__ __forceinline__ void load_sample(float2 (&v)[CH], const char *p)
 {
@@ -260,25 +287,25 @@ __device__ __forceinline__ void load_sample(float2 (&v)[CH], const char *p)
         if (CH % 2 == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 2; ++i) {
-                float4 q = __ldg((const float4 *)p + i);
+                float4 q = ldg_nc_f4((const float4 *)p + i);
                 v[2 * i] = make_float2(q.x, q.y); v[2 * i + 1] = make_float2(q.z, q.w);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = __ldg((const float2 *)p + i);
+            for (int i = 0; i < CH; ++i) v[i] = ldg_nc_f2((const float2 *)p + i);
         }
     } else {
         if (CH % 2 == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 2; ++i) {
-                uint2 raw = __ldg((const uint2 *)p + i);
+                uint2 raw = ldg_nc_u2((const uint2 *)p + i);
                 v[2 * i] = __half22float2(*reinterpret_cast<__half2 *>(&raw.x));
                 v[2 * i + 1] = __half22float2(*reinterpret_cast<__half2 *>(&raw.y));
             }
         } else {
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
-                unsigned raw = __ldg((const unsigned *)p + i);
+                unsigned raw = ldg_nc_u1((const unsigned *)p + i);
                 v[i] = __half22float2(*reinterpret_cast<__half2 *>(&raw));
             }
         }
@@ -358,7 +385,8 @@ __device__ __forceinline__ void gather_cell(float2 (&acc)[GS][CH], const GridLau
             float w = PLAIN ? kb_poly_xy(dx, dy, g.kb) : kb_weight_xy(dx, dy, g.kb);
             float sdc = fmaf(g.sdc_as, fabsf((float)ridx), g.sdc_bs);        /* tron.cu:412, times the scale */
             w *= (r == 0) ? sdc + sdc : sdc;             /* both loops visit r = 0 */
-            if (!(w > 0.f)) continue;                    /* the reference's wgt > 0 guard */
+            w = w > 0.f ? w : 0.f;                       /* the reference's wgt > 0 guard, branch-free so that
+                                                            the loads above are not sunk below it */
 #pragma unroll
             for (int s = 0; s < GS; ++s) {
                 if (GS == 1 || (mask >> s) & 1) {
