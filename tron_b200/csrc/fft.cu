@@ -30,6 +30,7 @@
  * plan-time table computed in double precision.
  */
 #include "tron_internal.h"
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
@@ -621,6 +622,163 @@ p2_fwd_pass_b(const float2 *__restrict__ tmp, float2 *__restrict__ grid, const f
     }
 }
 
+/* ====================================================================== */
+/* two-stage path: N = R1 * R2, R1 elements per thread, ONE exchange       */
+/* ====================================================================== */
+/*
+ * The radix-8 path above moves every element through shared memory three times for N = 512
+ * and is bound by that traffic.  Here a line is owned by T = N/R1 = R2 threads (half a warp
+ * for 512 = 32 x 16); thread j holds x[j + T q], q < R1:
+ *   stage 1  Y_j[k1] = DFT_R1 over q, in registers; written to shared memory (16-byte stores);
+ *   stage 2  for k1 = b: X[b + R1 k2] = DFT_R2 over j of w_N^(j b) Y_j[b], again in registers
+ *            (R1/R2 butterflies per thread).
+ * The threads of a line sit in one warp: the exchange needs __syncwarp() only.
+ * Exchange layout: Y_j[t] at j*(R1+2) + t -- the stores of a quarter-warp and the loads of a
+ * half-warp each touch every bank once.
+ */
+__device__ __forceinline__ float2 w32pow(int k, float s)      /* exp(s 2 pi i k / 32), k < 16 */
+{
+    const float c[16] = { 1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                          0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
+                          0.f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f,
+                          -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f };
+    const float n[16] = { 0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+                          0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+                          1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
+                          0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f };
+    return make_float2(c[k], s * n[k]);
+}
+/* radix-2 decimation in time on top of the half-size transform */
+template <int R> struct DftDit {
+    __device__ static void run(float2 *v, float s) {
+        float2 e[R / 2], o[R / 2];
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+        Dft<R / 2>::run(e, s); Dft<R / 2>::run(o, s);
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+            const float2 t = k == 0 ? o[0] : (k == R / 4 ? cmuli(o[k], s) : cmul(o[k], w32pow(k * (32 / R), s)));
+            v[k] = cadd(e[k], t); v[k + R / 2] = csub(e[k], t);
+        }
+    }
+};
+template <> struct Dft<16> { __device__ static void run(float2 *v, float s) { DftDit<16>::run(v, s); } };
+template <> struct Dft<32> { __device__ static void run(float2 *v, float s) { DftDit<32>::run(v, s); } };
+
+template <int N, int R1> struct P2W {
+    static constexpr int R2 = N / R1;
+    static constexpr int T = R2;                    /* threads per line */
+    static constexpr int M2 = R1 / R2;              /* stage-2 butterflies per thread */
+    static constexpr int XP = R1 + 2;               /* exchange pitch of one stage-1 thread */
+    static constexpr int LPX = T * XP;              /* exchange pitch of a line */
+    static constexpr int THREADS = 128;             /* small CTAs: five fit the register file at 96 registers */
+    static constexpr int L = THREADS / T;           /* lines per CTA */
+    static_assert(R1 >= R2 && R1 % R2 == 0 && T <= 32 && R1 <= 32, "unsupported split");
+};
+
+template <int N, int R1, int SGN>
+__device__ __forceinline__ void p2w_stage1(float2 (&v)[R1], float2 *xline, int j)
+{
+    Dft<R1>::run(v, (float)SGN);
+    float4 *d = reinterpret_cast<float4 *>(xline + j * P2W<N, R1>::XP);
+#pragma unroll
+    for (int m = 0; m < R1 / 2; ++m) d[m] = make_float4(v[2 * m].x, v[2 * m].y, v[2 * m + 1].x, v[2 * m + 1].y);
+}
+
+/* butterfly b of stage 2: a[k2] = X[b + R1 k2].  tw = exp(+2 pi i k / N) (global table) */
+template <int N, int R1>
+__device__ __forceinline__ void p2w_stage2_load(float2 (&a)[N / R1], const float2 *xline, int b)
+{
+    constexpr int R2 = N / R1, XP = P2W<N, R1>::XP;
+#pragma unroll
+    for (int t = 0; t < R2; ++t) a[t] = xline[t * XP + b];
+}
+template <int N, int R1, int SGN>
+__device__ __forceinline__ void p2w_stage2(float2 (&a)[N / R1], int b, const float2 *__restrict__ tw)
+{
+    constexpr int R2 = N / R1;
+    /* w^t, t < R2: the powers of two come from the table, the rest are products of depth <= 3 */
+    float2 w[R2];
+#pragma unroll
+    for (int t = 1; t < R2; t <<= 1) {
+        w[t] = __ldg(tw + b * t);
+        if (SGN < 0) w[t].y = -w[t].y;
+    }
+#pragma unroll
+    for (int t = 3; t < R2; ++t) {
+        if ((t & (t - 1)) == 0) continue;
+        int hi = 1; while (hi * 2 <= t) hi *= 2;      /* t = hi + lo, lo < hi */
+        w[t] = cmul(w[hi], w[t - hi]);
+    }
+#pragma unroll
+    for (int t = 1; t < R2; ++t) a[t] = cmul(a[t], w[t]);
+    Dft<R2>::run(a, (float)SGN);
+}
+
+/* adjoint pass A: grid[plane][y][:] --FFT--> keep nkeep centre outputs --> tmp[plane][a][y].
+ * The kept outputs are staged as F[line][a] (odd pitch) over the exchange buffer for the
+ * transposed, coalesced store. */
+template <int N, int R1>
+__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 5)
+p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep)
+{
+    extern __shared__ float2 smem[];
+    using G = P2W<N, R1>;
+    const int l = threadIdx.x / G::T, j = threadIdx.x % G::T;
+    float2 *xline = smem + l * G::LPX;
+    float2 *F = smem;
+    const int PF = nkeep | 1;
+    const int y0 = blockIdx.x * G::L;
+    const size_t plane = blockIdx.y;
+    const float2 *g = grid + plane * (size_t)N * N + (size_t)(y0 + l) * N + j;
+    {
+        float2 v[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) v[q] = g[q * G::T];
+        p2w_stage1<N, R1, +1>(v, xline, j);
+    }
+    __syncwarp();
+    float2 a[G::M2][G::R2];
+#pragma unroll
+    for (int m = 0; m < G::M2; ++m) p2w_stage2_load<N, R1>(a[m], xline, j + m * G::T);
+    __syncthreads();                                  /* exchange buffer consumed: F may overwrite it */
+    const int shift = N / 2 - (N - nkeep) / 2;       /* output a of frequency k: a = (k + shift) mod N */
+#pragma unroll
+    for (int m = 0; m < G::M2; ++m) {
+        const int b = j + m * G::T;
+        p2w_stage2<N, R1, +1>(a[m], b, tw);
+        const float sg = (b & 1) ? -1.f : 1.f;       /* input shift by N/2 = (-1)^k on the output */
+#pragma unroll
+        for (int t = 0; t < G::R2; ++t) {
+            const int aa = (b + t * R1 + shift) & (N - 1);
+            if (aa < nkeep) F[l * PF + aa] = make_float2(a[m][t].x * sg, a[m][t].y * sg);
+        }
+    }
+    __syncthreads();
+    float2 *out = tmp + plane * (size_t)nkeep * N + y0;
+    for (int idx = threadIdx.x; idx < nkeep * G::L; idx += G::THREADS) {
+        const int aa = idx / G::L, ll = idx % G::L;
+        out[(size_t)aa * N + ll] = F[ll * PF + aa];
+    }
+}
+
+template <int N, int R1> struct P2WLaunch {
+    using G = P2W<N, R1>;
+    static size_t smem_a(int nkeep) { return (size_t)std::max(G::L * G::LPX, G::L * (nkeep | 1)) * sizeof(float2); }
+    static int prepare()
+    {
+        TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_a<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
+        return 0;
+    }
+    static int adj_a(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
+    {
+        dim3 ga(N / G::L, a.nslices * a.nch);
+        p2w_adj_pass_a<N, R1><<<ga, G::THREADS, smem_a(f.nkeep), s>>>(a.grid, a.tmp, f.tw, f.nkeep);
+        TRON_CUDA(cudaGetLastError());
+        return 0;
+    }
+};
+
 template <int N, int L> struct P2Launch {
     static constexpr size_t SMEM = (size_t)(2 * L * P2<N, L>::PITCH + N + N / 8 + 1) * sizeof(float2);
     static constexpr int THREADS = L * (N / 8);
@@ -631,13 +789,20 @@ template <int N, int L> struct P2Launch {
         TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_b<N, L, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         TRON_CUDA(cudaFuncSetAttribute(p2_fwd_pass_a<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         TRON_CUDA(cudaFuncSetAttribute(p2_fwd_pass_b<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        if constexpr (N == 512) { int rc = P2WLaunch<512, 32>::prepare(); if (rc) return rc; }
         return 0;
     }
     static int adj(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
     {
-        dim3 ga(N / L, a.nslices * a.nch);
-        p2_adj_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.grid, a.tmp, f.tw, f.nkeep);
-        TRON_CUDA(cudaGetLastError());
+        bool wide_a = false;
+        if constexpr (N == 512) wide_a = getenv("TRON_FFT_R8") == nullptr;
+        if (wide_a) {
+            if constexpr (N == 512) { int rc = P2WLaunch<512, 32>::adj_a(f, a, s); if (rc) return rc; }
+        } else {
+            dim3 ga(N / L, a.nslices * a.nch);
+            p2_adj_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.grid, a.tmp, f.tw, f.nkeep);
+            TRON_CUDA(cudaGetLastError());
+        }
         dim3 gb((f.nkeep + L - 1) / L, a.nslices);
         if (2 * f.nkeep <= N)
             p2_adj_pass_b<N, L, 4><<<gb, THREADS, SMEM, s>>>(a.tmp, a.out, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total,
