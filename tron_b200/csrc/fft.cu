@@ -762,12 +762,94 @@ p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const 
     }
 }
 
+/* adjoint pass B for the usual 2x oversampling (nkeep = N/2), coils combined by sum of squares:
+ * tmp[slice][ch][b][:] --FFT--> keep N/2 centre outputs, |.|^2 summed over the coils in registers
+ * (a thread owns the same outputs for every coil), deapodised and stored once at the end.
+ * mode 0: image = (sqrt(sum), 0) (tron.cu:255-268); mode 3: the partial sum itself (coil shards). */
+template <int N, int R1>
+__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 4)
+p2w_adj_pass_b_sos(const float2 *__restrict__ tmp, void *__restrict__ outv, const float *__restrict__ deapod,
+                   const float2 *__restrict__ tw, int nch, int mode, int half_out)
+{
+    extern __shared__ float2 smem[];
+    using G = P2W<N, R1>;
+    constexpr int nkeep = N / 2, KT = G::R2 / 4;      /* kept k2: [0, KT) and [R2 - KT, R2) */
+    const int l = threadIdx.x / G::T, j = threadIdx.x % G::T;
+    float2 *xline = smem + l * G::LPX;
+    const int b0 = blockIdx.x * G::L;
+    const int slice = blockIdx.y;
+    float acc[G::M2][2 * KT];
+#pragma unroll
+    for (int m = 0; m < G::M2; ++m)
+#pragma unroll
+        for (int u = 0; u < 2 * KT; ++u) acc[m][u] = 0.f;
+    const float2 *src = tmp + ((size_t)slice * nch * nkeep + b0 + l) * (size_t)N + j;
+    for (int ch = 0; ch < nch; ++ch) {
+        {
+            float2 v[R1];
+#pragma unroll
+            for (int q = 0; q < R1; ++q) v[q] = src[q * G::T];
+            p2w_stage1<N, R1, +1>(v, xline, j);
+        }
+        src += (size_t)nkeep * N;
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < G::M2; ++m) {
+            const int b = j + m * G::T;
+            float2 a[G::R2];
+            p2w_stage2_load<N, R1>(a, xline, b);
+            p2w_stage2<N, R1, +1>(a, b, tw);
+#pragma unroll
+            for (int u = 0; u < 2 * KT; ++u) {
+                const int t = u < KT ? u : G::R2 - 2 * KT + u;
+                acc[m][u] = fmaf(a[t].x, a[t].x, fmaf(a[t].y, a[t].y, acc[m][u]));
+            }
+        }
+        __syncwarp();                                 /* the line's exchange buffer is free again */
+    }
+    /* stage the sums as S[line][a] for the transposed store; a = (k + N/4) mod N for the kept k */
+    float *S = reinterpret_cast<float *>(smem);
+    constexpr int PS = nkeep + 1;
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < G::M2; ++m)
+#pragma unroll
+        for (int u = 0; u < 2 * KT; ++u) {
+            const int t = u < KT ? u : G::R2 - 2 * KT + u;
+            const int aa = (j + m * G::T + t * R1 + N / 4) & (N - 1);
+            S[l * PS + aa] = acc[m][u];
+        }
+    __syncthreads();
+    const size_t img = (size_t)nkeep * nkeep;
+    for (int idx = threadIdx.x; idx < nkeep * G::L; idx += G::THREADS) {
+        const int aa = idx / G::L, ll = idx % G::L;
+        const size_t pix = (size_t)aa * nkeep + b0 + ll;
+        const float d = __ldg(deapod + pix);
+        const float sum = S[ll * PS + aa] * d * d;
+        if (mode == 3) ((float *)outv)[(size_t)slice * img + pix] = sum;
+        else {
+            const float2 val = make_float2(sqrtf(sum), 0.f);              /* tron.cu:263-264 */
+            if (half_out) ((__half2 *)outv)[(size_t)slice * img + pix] = __float22half2_rn(val);
+            else ((float2 *)outv)[(size_t)slice * img + pix] = val;
+        }
+    }
+}
+
 template <int N, int R1> struct P2WLaunch {
     using G = P2W<N, R1>;
     static size_t smem_a(int nkeep) { return (size_t)std::max(G::L * G::LPX, G::L * (nkeep | 1)) * sizeof(float2); }
     static int prepare()
     {
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_a<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
+        TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_b_sos<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N / 2)));
+        return 0;
+    }
+    /* sum-of-squares pass B; only for nkeep = N/2 and modes 0 / 3 */
+    static int adj_b_sos(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
+    {
+        dim3 gb(f.nkeep / G::L, a.nslices);
+        p2w_adj_pass_b_sos<N, R1><<<gb, G::THREADS, smem_a(N / 2), s>>>(a.tmp, a.out, a.deapod, f.tw, a.nch, a.mode, a.half_out);
+        TRON_CUDA(cudaGetLastError());
         return 0;
     }
     static int adj_a(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
@@ -802,6 +884,9 @@ template <int N, int L> struct P2Launch {
             dim3 ga(N / L, a.nslices * a.nch);
             p2_adj_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.grid, a.tmp, f.tw, f.nkeep);
             TRON_CUDA(cudaGetLastError());
+        }
+        if constexpr (N == 512) {
+            if (wide_a && 2 * f.nkeep == N && (a.mode == 0 || a.mode == 3)) return P2WLaunch<512, 32>::adj_b_sos(f, a, s);
         }
         dim3 gb((f.nkeep + L - 1) / L, a.nslices);
         if (2 * f.nkeep <= N)
