@@ -80,6 +80,29 @@ def test_pipeline_vs_oracle(lib, oracle, name):
     assert rel_l2(got, want) <= TOL_F32, rel_l2(got, want)
 
 
+@pytest.mark.parametrize("dims,flags", [
+    ([6, 1, 512, 60, 1], dict(adjoint=True, golden=True)),                                      # 512-point lines, RSS
+    ([6, 1, 512, 90, 1], dict(adjoint=True, golden=True, undersamp=0.1, prof_slide=13)),        # sliding windows
+    ([4, 1, 256, 48, 1], dict(adjoint=True, golden=True)),                                      # 256-point lines
+    ([1, 1, 512, 64, 1], dict(adjoint=True)),                                                   # complex output
+    ([2, 1, 512, 64, 1], dict(adjoint=True, gridos=1.0)),                                       # nothing cropped
+])
+@pytest.mark.parametrize("radix8", [False, True])
+def test_pipeline_line_lengths_of_the_benchmarks(lib, reflib, dims, flags, radix8, monkeypatch):
+    """The 256- and 512-point transforms have two implementations (two-stage 16x16 / 32x16 and
+    radix-8, fft.cu); both must match the reference on the grids the benchmark configs use."""
+    import tron_b200 as t
+    torch_cuda()
+    if radix8:
+        monkeypatch.setenv("TRON_FFT_R8", "1")
+    h_in = synth_complex((int(np.prod(dims)),), stream=77)
+    want = run_ref(reflib, dims, flags, h_in)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        got = p.recon_host(h_in)
+    assert got.shape == want.shape
+    assert rel_l2(got, want) <= TOL_F32, rel_l2(got, want)
+
+
 def test_pipeline_more_than_six_coils(lib, reflib_wide):
     """nc > MAXCHAN needs the widened reference build (tron.h:51)."""
     import tron_b200 as t

@@ -861,6 +861,9 @@ template <int N, int R1> struct P2WLaunch {
     }
 };
 
+/* line lengths served by the two-stage path: elements per thread (0: radix-8 path only) */
+template <int N> struct P2WSplit { static constexpr int R1 = N == 512 ? 32 : (N == 256 ? 16 : 0); };
+
 template <int N, int L> struct P2Launch {
     static constexpr size_t SMEM = (size_t)(2 * L * P2<N, L>::PITCH + N + N / 8 + 1) * sizeof(float2);
     static constexpr int THREADS = L * (N / 8);
@@ -871,22 +874,22 @@ template <int N, int L> struct P2Launch {
         TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_b<N, L, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         TRON_CUDA(cudaFuncSetAttribute(p2_fwd_pass_a<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         TRON_CUDA(cudaFuncSetAttribute(p2_fwd_pass_b<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        if constexpr (N == 512) { int rc = P2WLaunch<512, 32>::prepare(); if (rc) return rc; }
+        if constexpr (P2WSplit<N>::R1 != 0) { int rc = P2WLaunch<N, P2WSplit<N>::R1>::prepare(); if (rc) return rc; }
         return 0;
     }
     static int adj(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
     {
         bool wide_a = false;
-        if constexpr (N == 512) wide_a = getenv("TRON_FFT_R8") == nullptr;
+        if constexpr (P2WSplit<N>::R1 != 0) wide_a = getenv("TRON_FFT_R8") == nullptr;
         if (wide_a) {
-            if constexpr (N == 512) { int rc = P2WLaunch<512, 32>::adj_a(f, a, s); if (rc) return rc; }
+            if constexpr (P2WSplit<N>::R1 != 0) { int rc = P2WLaunch<N, P2WSplit<N>::R1>::adj_a(f, a, s); if (rc) return rc; }
         } else {
             dim3 ga(N / L, a.nslices * a.nch);
             p2_adj_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.grid, a.tmp, f.tw, f.nkeep);
             TRON_CUDA(cudaGetLastError());
         }
-        if constexpr (N == 512) {
-            if (wide_a && 2 * f.nkeep == N && (a.mode == 0 || a.mode == 3)) return P2WLaunch<512, 32>::adj_b_sos(f, a, s);
+        if constexpr (P2WSplit<N>::R1 != 0) {
+            if (wide_a && 2 * f.nkeep == N && (a.mode == 0 || a.mode == 3)) return P2WLaunch<N, P2WSplit<N>::R1>::adj_b_sos(f, a, s);
         }
         dim3 gb((f.nkeep + L - 1) / L, a.nslices);
         if (2 * f.nkeep <= N)
