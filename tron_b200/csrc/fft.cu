@@ -673,6 +673,13 @@ template <int N, int R1> struct P2W {
     static constexpr int LPX = T * XP;              /* exchange pitch of a line */
     static constexpr int THREADS = 128;             /* small CTAs: five fit the register file at 96 registers */
     static constexpr int L = THREADS / T;           /* lines per CTA */
+    /* pitch of the staged kept outputs F[line][a]: the transposed read of a half-warp covers L lines x
+     * 16/L consecutive outputs and must touch 16 distinct 8-byte banks: pitch == 16/L (mod 16) */
+    __host__ __device__ static constexpr int fpitch(int nkeep)
+    {
+        constexpr int want = L >= 16 ? 1 : 16 / L;
+        return nkeep + ((want - nkeep % 16) + 16) % 16;
+    }
     static_assert(R1 >= R2 && R1 % R2 == 0 && T <= 32 && R1 <= 32, "unsupported split");
 };
 
@@ -727,7 +734,7 @@ p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const 
     const int l = threadIdx.x / G::T, j = threadIdx.x % G::T;
     float2 *xline = smem + l * G::LPX;
     float2 *F = smem;
-    const int PF = nkeep | 1;
+    const int PF = G::fpitch(nkeep);
     const int y0 = blockIdx.x * G::L;
     const size_t plane = blockIdx.y;
     const float2 *g = grid + plane * (size_t)N * N + (size_t)(y0 + l) * N + j;
@@ -837,7 +844,7 @@ p2w_adj_pass_b_sos(const float2 *__restrict__ tmp, void *__restrict__ outv, cons
 
 template <int N, int R1> struct P2WLaunch {
     using G = P2W<N, R1>;
-    static size_t smem_a(int nkeep) { return (size_t)std::max(G::L * G::LPX, G::L * (nkeep | 1)) * sizeof(float2); }
+    static size_t smem_a(int nkeep) { return (size_t)std::max(G::L * G::LPX, G::L * G::fpitch(nkeep)) * sizeof(float2); }
     static int prepare()
     {
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_a<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
