@@ -51,7 +51,7 @@ enum {
     TRON_ENODEV = -2,      /* no usable CUDA device */
     TRON_ECUDA = -3,       /* a CUDA runtime call failed */
     TRON_ENOMEM = -4,
-    TRON_EUNSUPPORTED = -5 /* valid in the reference's CLI but not implemented (-3, -i) */
+    TRON_EUNSUPPORTED = -5 /* valid in the reference's CLI but not implemented (-3; -i outside its domain) */
 };
 
 /* What main() reads from the RA header and getopt (tron.cu:822-874, 905-961). */
@@ -64,7 +64,7 @@ typedef struct tron_config {
     float data_undersamp;   /* -u  (default 1) */
     int   prof_slide;       /* -d  (default 0 = npe1work) */
     int   skip_angles;      /* -s */
-    int   niter;            /* -i  (CGNR; must be 0) */
+    int   niter;            /* -i  CGNR iterations (adjoint only, gridos 2; tron.cu:665-720, see cgnr.cu) */
     int   koosh;            /* -3  (must be 0: the reference has no 3-D kernels) */
     int   verbose;          /* -v */
     int   device;           /* -g  (-1 = leave the current device alone) */
@@ -80,6 +80,10 @@ typedef struct tron_config {
     int   batch_slices;     /* slices per kernel launch, 0 = auto */
     int   per_coil_out;     /* adjoint: skip the coil combine, emit [nx*ny*nc] per slice
                                (what tron_nufft_adj_radial2d returns in the reference) */
+    int   coil_combine;     /* adjoint, nc>1: 0 = root sum of squares (tron.cu:764), 1 = adaptive Walsh
+                               combine (coilcombinewalsh, tron.cu:270-302; its call at tron.cu:766 is
+                               commented out in the reference) */
+    int   walsh_npatch;     /* patch half-width of the Walsh combine (tron.cu:766 passes 1) */
 } tron_config;
 
 /* Derived geometry, same names as the reference's globals (tron.cu:76-79). */
@@ -130,6 +134,14 @@ int  tron_recon_device(tron_plan *plan, void *d_out, const void *d_in, void *str
 int  tron_grid_device(tron_plan *plan, void *d_grid, const void *d_samples, int z0, int nslices, void *stream);
 int  tron_grid_to_interleaved(tron_plan *plan, void *d_dst, const void *d_grid, int nslices, void *stream);
 int  tron_degrid_device(tron_plan *plan, void *d_samples, const void *d_grid, void *stream);
+/* Coil combination alone, on channel-interleaved per-coil images [nslices][nimg][nimg][nchan]
+ * (complex64) -> [nslices][nimg][nimg] complex64.  No plan needed.
+ * tron_coilcombine_sos_device:   coilcombinesos   (tron.cu:255-268)
+ * tron_coilcombine_walsh_device: coilcombinewalsh (tron.cu:270-302, powit tron.cu:222-253); unlike the
+ *   reference (MAXCHAN = 6, tron.h:51) any nchan <= 128 works. */
+int  tron_coilcombine_sos_device(void *d_img, const void *d_coilimg, int nimg, int nchan, int nslices, void *stream);
+int  tron_coilcombine_walsh_device(void *d_img, const void *d_coilimg, int nimg, int nchan, int npatch,
+                                   int nslices, void *stream);
 /* average device milliseconds of the last tron_recon_* call's stages:
  * ms[0] = gridding/degridding kernels, ms[1] = FFT passes, ms[2] = everything else on the stream */
 int  tron_plan_last_stage_ms(tron_plan *plan, float ms[3]);
@@ -158,6 +170,13 @@ void tron_nufft_adj_radial2d(tron_float2 *d_out, tron_float2 *d_in, const int j)
 void tron_nufft_radial2d(tron_float2 *d_out, tron_float2 *d_in, const int j);       /* tron.cu:639 */
 void recon_radial2d(tron_float2 *h_outdata, const tron_float2 *h_indata);           /* tron.cu:726 */
 void recon_radial_2d(tron_float2 *h_outdata, const tron_float2 *h_indata);          /* tron.h:71 spelling */
+/* tron.cu:665: `niter` CGNR iterations on one window already on the device -> per-coil images
+ * [nx*ny*nc] in d_out (the reference then coil-combines them, tron.cu:764) */
+void tron_cgnr_radial2d(tron_float2 *d_out, tron_float2 *d_in, const int j, const int niter);
+/* tron.cu:651-663: device-to-device copy on the plan's stream and z = y + alpha x */
+void copy(tron_float2 *d_dst, tron_float2 *d_src, const size_t N, const int j);
+int  tron_launch_Caxpy(void *d_z, const void *d_y, const void *d_x, float alpha, size_t N,
+                       int blocks, int threads, void *stream);
 
 /* host launchers for the two compatibility kernels below (FFI users have no <<<>>>) */
 int  tron_launch_gridradial2d(void *udata, const void *nudata, int nxos, int nchan, int nro, int npe,
@@ -176,6 +195,7 @@ __global__ void gridradial2d(float2 *udata, const float2 *__restrict__ nudata, c
 __global__ void degridradial2d(float2 *nudata, const float2 *__restrict__ udata, const int nimg,
                                const int nchan, const int nro, const int npe, const float kernwidth,
                                const float gridos, const int skip_angles, const int flag_golden_angle);
+__global__ void Caxpy(float2 *d_z, float2 *d_y, float2 *d_x, float alpha, const size_t N);   /* tron.cu:658 */
 #endif
 
 #ifdef __cplusplus

@@ -24,7 +24,8 @@ class _Cfg(C.Structure):
                 ("nc", C.c_int), ("nt", C.c_int), ("nro", C.c_int), ("npe1", C.c_int),
                 ("npe2", C.c_int), ("npe1work", C.c_int),
                 ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("nxos", C.c_int), ("nyos", C.c_int),
-                ("out_dims", C.c_uint64 * 5), ("out_elems", C.c_uint64)]
+                ("out_dims", C.c_uint64 * 5), ("out_elems", C.c_uint64),
+                ("niter", C.c_int), ("coil_combine", C.c_int), ("walsh_npatch", C.c_int)]
 
 
 def _ptr(a):
@@ -65,6 +66,9 @@ class Oracle:
         L.oracle_pad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.oracle_deapod.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]
         L.oracle_coilcombinesos.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_coilcombinewalsh.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.oracle_nufft_adj_coils.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_cgnr_coils.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.oracle_geometry.argtypes = [C.POINTER(_Cfg)]
         L.oracle_recon_radial2d.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_void_p]
         L.oracle_floatbits_to_halfbits.restype = C.c_uint16
@@ -77,7 +81,7 @@ class Oracle:
 
     # -- configuration ----------------------------------------------------
     def config(self, dims, adjoint, golden=False, gridos=2.0, kernwidth=2.0, undersamp=1.0,
-               prof_slide=0, skip_angles=0):
+               prof_slide=0, skip_angles=0, niter=0, coil_combine=0, walsh_npatch=1):
         cfg = _Cfg()
         self.lib.oracle_cfg_defaults(C.byref(cfg))
         for i, d in enumerate(dims):
@@ -85,6 +89,7 @@ class Oracle:
         cfg.adjoint = int(bool(adjoint)); cfg.golden_angle = int(bool(golden))
         cfg.gridos = gridos; cfg.kernwidth = kernwidth; cfg.data_undersamp = undersamp
         cfg.prof_slide = prof_slide; cfg.skip_angles = skip_angles
+        cfg.niter = int(niter); cfg.coil_combine = int(coil_combine); cfg.walsh_npatch = int(walsh_npatch)
         rc = self.lib.oracle_geometry(C.byref(cfg))
         if rc:
             raise ValueError("oracle_geometry rejected the configuration (%d)" % rc)
@@ -163,6 +168,23 @@ class Oracle:
         self.lib.oracle_coilcombinesos(_ptr(out), _ptr(_c(coilimg)), nimg, nchan)
         return out
 
+    def walsh(self, coilimg, nimg, nchan, npatch=1):
+        out = np.zeros((nimg, nimg), dtype=c64)
+        self.lib.oracle_coilcombinewalsh(_ptr(out), _ptr(_c(coilimg)), nimg, nchan, npatch)
+        return out
+
+    def adj_coils(self, cfg, samples, peoffset=0):
+        """Per-coil images (nx, nx, nc) of one adjoint slice (tron.cu:623-637)."""
+        out = np.zeros((cfg.nx, cfg.nx, cfg.nc), dtype=c64)
+        self.lib.oracle_nufft_adj_coils(C.byref(cfg), _ptr(out), _ptr(_c(samples)), peoffset)
+        return out
+
+    def cgnr_coils(self, cfg, samples, peoffset=0, niter=1):
+        """Per-coil images (nx, nx, nc) after `niter` CGNR iterations on one window."""
+        out = np.zeros((cfg.nx, cfg.nx, cfg.nc), dtype=c64)
+        self.lib.oracle_cgnr_coils(C.byref(cfg), _ptr(out), _ptr(_c(samples)), peoffset, niter)
+        return out
+
     def float_to_half_bits(self, bits):
         f = self.lib.oracle_floatbits_to_halfbits
         return np.array([f(int(b)) for b in np.asarray(bits, dtype=np.uint32).ravel()], dtype=np.uint16)
@@ -195,6 +217,9 @@ class RefLib:
         L.tronref_degrid.restype = C.c_float
         L.tronref_degrid.argtypes = L.tronref_grid.argtypes
         L.tronref_deapod.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]
+        if hasattr(L, "tronref_walsh"):
+            L.tronref_walsh.restype = C.c_float
+            L.tronref_walsh.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.tronref_adj_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
         L.tronref_geometry.argtypes = [C.POINTER(C.c_int)]
         L.tronref_maxchan.restype = C.c_int
@@ -250,6 +275,15 @@ class RefLib:
         a = _c(a).copy()
         self.lib.tronref_deapod(_ptr(a), n, nrep, m, sigma)
         return a
+
+    def walsh(self, coilimg, nimg, nchan, npatch=1, reps=0):
+        """The reference's coilcombinewalsh kernel (tron.cu:270-302) on (nimg, nimg, nchan) coil images.
+        It zeroes NCHAN^2 = 36 matrix entries whatever nchan is: defined for nchan <= 6 only."""
+        if nchan > 6:
+            raise ValueError("coilcombinewalsh is undefined for nchan > NCHAN = 6 (tron.cu:282)")
+        out = np.zeros((nimg, nimg), dtype=c64)
+        ms = self.lib.tronref_walsh(_ptr(out), _ptr(_c(coilimg)), nimg, nchan, npatch, reps)
+        return (out, ms) if reps else out
 
     def spoke_cs(self, n, npe, skip, golden, degrid):
         """(ct, st) of spokes 0..n-1 as the reference kernels compute them (SFU)."""

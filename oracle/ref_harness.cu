@@ -166,6 +166,25 @@ void tronref_deapod(float2 *h_a, int n, int nrep, float m, float sigma)
     cudaMemcpy(h_a, g_da, ne * sizeof(float2), cudaMemcpyDeviceToHost);
 }
 
+/* coilcombinewalsh alone (tron.cu:270-302; its call at tron.cu:766 is commented out in the
+ * reference): h_img[nimg*nimg] <- h_coil[nchan*nimg*nimg].  Returns ms per launch when reps > 0. */
+float tronref_walsh(float2 *h_img, const float2 *h_coil, int nimg, int nchan, int npatch, int reps)
+{
+    size_t ne = (size_t)nchan * nimg * nimg;
+    if (ensure(ne)) return -1.f;
+    cudaMemcpy(g_da, h_coil, ne * sizeof(float2), cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    coilcombinewalsh<<<blocks, threads>>>(g_db, g_da, nimg, nchan, 1, npatch);
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i)
+        coilcombinewalsh<<<blocks, threads>>>(g_db, g_da, nimg, nchan, 1, npatch);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    cudaMemcpy(h_img, g_db, (size_t)nimg * nimg * sizeof(float2), cudaMemcpyDeviceToHost);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return reps > 0 ? ms / reps : 0.f;
+}
+
 /* Per-stage device time of one adjoint slice with the configured geometry:
  * ms[0..7] = precompensate, gridradial2d, fftshift, cufft, fftshift, crop,
  * deapod, coilcombinesos.  Buffers and plans come from tron_init(). */

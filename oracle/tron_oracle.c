@@ -254,11 +254,21 @@ long oracle_grid_hits(int32_t *hits, long maxhits, int nxos, int nro, int npe,
 
 /* tron.cu:540-577.  X walks rows, Y walks columns; (n+1)/2 is an integer
  * division; taps wrap periodically; no output scaling. */
+static void degrid_with_trig(ocplx *nudata, const ocplx *udata, int n, int nrep,
+                             int nro, int npe, float W, const float *ct, const float *st);
+
 void oracle_degridradial2d(ocplx *nudata, const ocplx *udata, int n, int nrep,
                            int nro, int npe, float W, int skip_angles, int golden)
 {
     float *ct = (float *)malloc(sizeof(float) * (size_t)npe * 2), *st = ct + npe;
     spoke_tables(ct, st, npe, skip_angles, golden, 1);
+    degrid_with_trig(nudata, udata, n, nrep, nro, npe, W, ct, st);
+    free(ct);
+}
+
+static void degrid_with_trig(ocplx *nudata, const ocplx *udata, int n, int nrep,
+                             int nro, int npe, float W, const float *ct, const float *st)
+{
     const float c0 = (float)((n + 1) / 2);
 #pragma omp parallel for schedule(static)
     for (int id = 0; id < nro * npe; ++id) {
@@ -282,7 +292,6 @@ void oracle_degridradial2d(ocplx *nudata, const ocplx *udata, int n, int nrep,
             }
         }
     }
-    free(ct);
 }
 
 /* tron.cu:161-178: out-of-place circular shift; FORWARD moves by n/2,
@@ -430,6 +439,64 @@ void oracle_coilcombinesos(ocplx *img, const ocplx *coilimg, int nimg, int nchan
     }
 }
 
+/* tron.cu:222-253 (powit) and 270-302 (coilcombinewalsh): adaptive coil combine.
+ * Per pixel: A[c1][c2] = sum over the (2*npatch+1)^2 patch (clipped at the image
+ * border) of z_c1 * conj(z_c2), accumulated px-outer / py-inner; five power
+ * iterations from x = (1,..,1) with y/|y| as a multiplication by the float
+ * reciprocal (float2math.h:24-28); img = sum_c conj(x_c) * z_c.  The reference
+ * zeroes NCHAN*NCHAN = 36 entries whatever nchan is (tron.cu:282, tron.h:50), so
+ * it is only defined for nchan <= 6; this restatement zeroes nchan^2.  A patch of
+ * all zeros gives 0 * (1/0) = NaN in the reference and here. */
+void oracle_coilcombinewalsh(ocplx *img, const ocplx *coilimg, int nimg, int nchan, int npatch)
+{
+    if (nchan == 1) { memcpy(img, coilimg, sizeof(ocplx) * (size_t)nimg * nimg); return; }
+#pragma omp parallel
+    {
+        ocplx *A = (ocplx *)malloc(sizeof(ocplx) * (size_t)nchan * nchan);
+        ocplx *x = (ocplx *)malloc(sizeof(ocplx) * nchan), *y = (ocplx *)malloc(sizeof(ocplx) * nchan);
+#pragma omp for schedule(static)
+        for (long id = 0; id < (long)nimg * nimg; ++id) {
+            int px0 = (int)(id / nimg), py0 = (int)(id % nimg);
+            for (int k = 0; k < nchan * nchan; ++k) A[k].x = A[k].y = 0.f;
+            int xlo = px0 - npatch < 0 ? 0 : px0 - npatch, xhi = px0 + npatch > nimg - 1 ? nimg - 1 : px0 + npatch;
+            int ylo = py0 - npatch < 0 ? 0 : py0 - npatch, yhi = py0 + npatch > nimg - 1 ? nimg - 1 : py0 + npatch;
+            for (int px = xlo; px <= xhi; ++px)
+                for (int py = ylo; py <= yhi; ++py) {
+                    const ocplx *z = coilimg + (size_t)nchan * ((size_t)px * nimg + py);
+                    for (int c2 = 0; c2 < nchan; ++c2)
+                        for (int c1 = 0; c1 < nchan; ++c1) {     /* a * conj(b), float2math.h:38-42 */
+                            float ax = z[c1].x, ay = z[c1].y, bx = z[c2].x, by = -z[c2].y;
+                            A[c1 * nchan + c2].x += ax * bx - ay * by;
+                            A[c1 * nchan + c2].y += ax * by + ay * bx;
+                        }
+                }
+            for (int k = 0; k < nchan; ++k) { x[k].x = 1.f; x[k].y = 0.f; }
+            for (int t = 0; t < 5; ++t) {                        /* tron.cu:291: powit(A, nchan, 5) */
+                float nsq = 0.f;
+                for (int j = 0; j < nchan; ++j) {
+                    y[j].x = y[j].y = 0.f;
+                    for (int k = 0; k < nchan; ++k) {
+                        ocplx a = A[j * nchan + k];
+                        y[j].x += a.x * x[k].x - a.y * x[k].y;
+                        y[j].y += a.x * x[k].y + a.y * x[k].x;
+                    }
+                }
+                for (int k = 0; k < nchan; ++k) nsq += y[k].x * y[k].x + y[k].y * y[k].y;
+                float inv = 1.0f / sqrtf(nsq);
+                for (int k = 0; k < nchan; ++k) { x[k].x = y[k].x * inv; x[k].y = y[k].y * inv; }
+            }
+            ocplx o = {0.f, 0.f};
+            const ocplx *z = coilimg + (size_t)nchan * id;
+            for (int c = 0; c < nchan; ++c) {                    /* conj(x_c) * z_c, tron.cu:294 */
+                o.x += x[c].x * z[c].x - (-x[c].y) * z[c].y;
+                o.y += x[c].x * z[c].y + (-x[c].y) * z[c].x;
+            }
+            img[id] = o;
+        }
+        free(A); free(x); free(y);
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* geometry and pipelines                                              */
 /* ------------------------------------------------------------------ */
@@ -471,9 +538,10 @@ int oracle_geometry(oracle_cfg *c)
     return 0;
 }
 
-/* tron.cu:623-637 then 764: one adjoint slice.  samples points at the first
- * spoke of the window; peoffset enters only the golden-angle index. */
-void oracle_nufft_adj_slice(const oracle_cfg *c, ocplx *img_out, const ocplx *samples, int peoffset)
+/* tron.cu:623-637: the per-coil images of one adjoint slice (what tron_nufft_adj_radial2d
+ * returns).  samples points at the first spoke of the window; peoffset enters only the
+ * golden-angle index. */
+static void adj_coils_impl(const oracle_cfg *c, ocplx *coilimg_out, const ocplx *samples, int peoffset, int matched)
 {
     int nchan = c->nc * c->nt, n = c->nxos;
     size_t ns = (size_t)nchan * c->nro * c->npe1work, ng = (size_t)nchan * n * n;
@@ -486,10 +554,135 @@ void oracle_nufft_adj_slice(const oracle_cfg *c, ocplx *img_out, const ocplx *sa
     oracle_fftshift(u, v, n, nchan, 1);
     oracle_fft2(u, n, nchan, +1);                          /* CUFFT_INVERSE */
     oracle_fftshift(v, u, n, nchan, 0);
-    oracle_crop(u, c->nx, v, n, nchan);
-    oracle_deapod(u, c->nx, nchan, c->kernwidth, c->gridos);
-    oracle_coilcombinesos(img_out, u, c->nx, c->nc);
+    if (!matched) {
+        oracle_crop(u, c->nx, v, n, nchan);
+        oracle_deapod(u, c->nx, nchan, c->kernwidth, c->gridos);
+    } else {                                               /* the forward model's weights (tron.cu:643) */
+        oracle_deapod(v, n, nchan, c->kernwidth, 1.f);
+        oracle_crop(u, c->nx, v, n, nchan);
+    }
+    memcpy(coilimg_out, u, sizeof(ocplx) * (size_t)nchan * c->nx * c->nx);
     free(u); free(v);
+}
+
+void oracle_nufft_adj_coils(const oracle_cfg *c, ocplx *coilimg_out, const ocplx *samples, int peoffset)
+{
+    adj_coils_impl(c, coilimg_out, samples, peoffset, 0);
+}
+
+/* tron.cu:764 (root sum of squares) or the disabled call at tron.cu:766 (Walsh) */
+static void combine_coils(const oracle_cfg *c, ocplx *img_out, const ocplx *coilimg)
+{
+    if (c->coil_combine == 1) oracle_coilcombinewalsh(img_out, coilimg, c->nx, c->nc, c->walsh_npatch);
+    else oracle_coilcombinesos(img_out, coilimg, c->nx, c->nc);
+}
+
+/* tron.cu:639-649 with the spoke angles of the GRIDDING operator (tron.cu:509, absolute index
+ * skip + peoffset): the forward model that the adjoint of window `peoffset` is the adjoint of.
+ * The reference's CGNR calls tron_nufft_radial2d, whose angles ignore peoffset and, for linear
+ * angles, follow a different formula (tron.cu:555) -- one of the reasons it is marked
+ * "NOT WORKING CORRECTLY YET" (tron.cu:670). */
+static void fwd_coils_grid_angles(const oracle_cfg *c, ocplx *samples_out, const ocplx *coilimg, int peoffset)
+{
+    int nchan = c->nc * c->nt, n = c->nxos, npe = c->npe1work;
+    size_t ng = (size_t)nchan * n * n, ns = (size_t)nchan * c->nro * npe;
+    ocplx *u = (ocplx *)malloc(sizeof(ocplx) * (ns > ng ? ns : ng));
+    ocplx *v = (ocplx *)malloc(sizeof(ocplx) * (ns > ng ? ns : ng));
+    float *ct = (float *)malloc(sizeof(float) * (size_t)npe * 2), *st = ct + npe;
+    oracle_pad(v, n, coilimg, c->nx, nchan);
+    oracle_deapod(v, n, nchan, c->kernwidth, 1.f);
+    oracle_fftshift(u, v, n, nchan, 0);
+    oracle_fft2(u, n, nchan, -1);
+    oracle_fftshift(v, u, n, nchan, 1);
+    spoke_tables(ct, st, npe, c->skip_angles + peoffset, c->golden_angle, 0);
+    degrid_with_trig(samples_out, v, n, nchan, c->nro, npe, c->kernwidth, ct, st);
+    free(u); free(v); free(ct);
+}
+
+/* Conjugate gradients on the weighted normal equations (-i niter): the algorithm tron.cu:665-720
+ * names (Knopp et al. 2007, Algorithm 1), restated so that it converges.  The reference's own
+ * version is self-declared broken (tron.cu:670): norms where squared norms belong, image vectors
+ * sized nxos^2 although the adjoint returns nx^2, a byte-count memset, forward angles without
+ * peoffset, and an operator pair that is not an adjoint pair.  What is restated here keeps the
+ * reference's two operators and repairs exactly what breaks the symmetry of B A:
+ *   A  = forward model above (pad, deapod(nxos, 1), FFT, degrid with the gridding angles);
+ *   B  = tron_nufft_adj_radial2d with the FORWARD model's deapodisation weights (tron.cu:643
+ *        instead of 635: the two tables differ by the F9 coordinate quirk), and with row 0 and
+ *        column 0 of its output cleared, because pad drops them (tron.cu:449-450), so
+ *        B = s A^H W', s = 1/(nxos npe1work) (tron.cu:532);
+ *   W' = the weights gridding really applies: the ramp of precompensate (tron.cu:405-416),
+ *        doubled at ro = nro/2 (r = 0 is visited twice, tron.cu:512,521) and zero at ro = 0
+ *        (r = -nro/2 lies outside Rhi <= nxos/2-1, tron.cu:499).  Needs nro == nxos.
+ *     r = M y (M clears ro = 0);  z = B r;  p = z;  x = 0
+ *     repeat niter times:  v = A p;  alpha = |z|^2 / (s <v, W' v>);  x += alpha p
+ *                          (the last iteration stops here)
+ *                          r -= alpha M v;  z' = B r;  beta = |z'|^2 / |z|^2;  p = z' + beta p;  z = z'
+ * What remains unsymmetric is the annulus clipping of gridding (F4, ~6e-4 of <r, A p>).  All coils
+ * share alpha and beta (the vectors hold every coil, as in tron.cu:679-680); inner products are
+ * accumulated in double.  x (per-coil images) is then coil-combined. */
+static void zero_first_row_col(ocplx *z, int nx, int nchan)
+{
+    for (int i = 0; i < nx; ++i)
+        for (int ch = 0; ch < nchan; ++ch) {
+            z[(size_t)nchan * i + ch].x = z[(size_t)nchan * i + ch].y = 0.f;                       /* row 0 */
+            z[(size_t)nchan * ((size_t)i * nx) + ch].x = z[(size_t)nchan * ((size_t)i * nx) + ch].y = 0.f;   /* column 0 */
+        }
+}
+
+void oracle_cgnr_coils(const oracle_cfg *c, ocplx *x, const ocplx *samples, int peoffset, int niter)
+{
+    int nchan = c->nc * c->nt;
+    size_t N = (size_t)nchan * c->nx * c->nx, n = (size_t)nchan * c->nro * c->npe1work;
+    ocplx *r = (ocplx *)malloc(sizeof(ocplx) * n), *v = (ocplx *)malloc(sizeof(ocplx) * n);
+    ocplx *z = (ocplx *)malloc(sizeof(ocplx) * N), *p = (ocplx *)malloc(sizeof(ocplx) * N);
+    const float s = 1.f / (float)c->nxos / (float)c->npe1work;
+    const float wa = (2.f - 2.f / (float)c->npe1work) / (float)c->nro, wb = 1.f / (float)c->npe1work;
+    memcpy(r, samples, sizeof(ocplx) * n);
+    for (size_t i = 0; i < n; ++i)                         /* ro = 0 has weight 0 in W' */
+        if ((i / (size_t)nchan) % (size_t)c->nro == 0) r[i].x = r[i].y = 0.f;
+    adj_coils_impl(c, z, r, peoffset, 1);
+    zero_first_row_col(z, c->nx, nchan);
+    memcpy(p, z, sizeof(ocplx) * N);
+    memset(x, 0, sizeof(ocplx) * N);
+    double zz = 0.0;
+    for (size_t i = 0; i < N; ++i) zz += (double)z[i].x * z[i].x + (double)z[i].y * z[i].y;
+    for (int t = 0; t < niter; ++t) {
+        fwd_coils_grid_angles(c, v, p, peoffset);
+        double vwv = 0.0;
+        for (size_t i = 0; i < n; ++i) {
+            int ro = (int)((i / (size_t)nchan) % (size_t)c->nro);
+            float w = wa * fabsf((float)ro - (float)(c->nro / 2)) + wb;
+            if (ro == c->nro / 2) w += w;                  /* gridding visits r = 0 twice (tron.cu:512,521) */
+            if (ro == 0) w = 0.f;                          /* r = -nro/2 lies outside Rhi <= nxos/2-1 (tron.cu:499) */
+            vwv += (double)w * ((double)v[i].x * v[i].x + (double)v[i].y * v[i].y);
+        }
+        float alpha = vwv > 0.0 ? (float)(zz / ((double)s * vwv)) : 0.f;
+        for (size_t i = 0; i < N; ++i) { x[i].x += alpha * p[i].x; x[i].y += alpha * p[i].y; }
+        if (t == niter - 1) break;
+        for (size_t i = 0; i < n; ++i) {
+            if ((i / (size_t)nchan) % (size_t)c->nro == 0) continue;
+            r[i].x -= alpha * v[i].x; r[i].y -= alpha * v[i].y;
+        }
+        adj_coils_impl(c, z, r, peoffset, 1);
+        zero_first_row_col(z, c->nx, nchan);
+        double zz2 = 0.0;
+        for (size_t i = 0; i < N; ++i) zz2 += (double)z[i].x * z[i].x + (double)z[i].y * z[i].y;
+        float beta = zz > 0.0 ? (float)(zz2 / zz) : 0.f;
+        for (size_t i = 0; i < N; ++i) { p[i].x = z[i].x + beta * p[i].x; p[i].y = z[i].y + beta * p[i].y; }
+        zz = zz2;
+    }
+    free(r); free(v); free(z); free(p);
+}
+
+/* tron.cu:753-764: one adjoint slice = (CGNR | plain adjoint) then the coil combine */
+void oracle_nufft_adj_slice(const oracle_cfg *c, ocplx *img_out, const ocplx *samples, int peoffset)
+{
+    int nchan = c->nc * c->nt;
+    ocplx *u = (ocplx *)malloc(sizeof(ocplx) * (size_t)nchan * c->nx * c->nx);
+    if (c->niter > 0) oracle_cgnr_coils(c, u, samples, peoffset, c->niter);
+    else oracle_nufft_adj_coils(c, u, samples, peoffset);
+    combine_coils(c, img_out, u);
+    free(u);
 }
 
 /* tron.cu:639-649: one forward slice. */

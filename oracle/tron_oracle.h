@@ -47,6 +47,10 @@ typedef struct {
     int nx, ny, nz, nxos, nyos;
     uint64_t out_dims[5];
     uint64_t out_elems;      /* number of complex elements of the output */
+    /* extensions, 0 = the reference's executed path */
+    int niter;               /* -i: CGNR iterations (tron.cu:665-720, restated so that it converges) */
+    int coil_combine;        /* 0 root sum of squares (tron.cu:764), 1 Walsh adaptive combine (tron.cu:270-302, 766) */
+    int walsh_npatch;        /* patch half-width of the Walsh combine (tron.cu:766 passes 1) */
 } oracle_cfg;
 
 void oracle_cfg_defaults(oracle_cfg *c);
@@ -75,6 +79,7 @@ void oracle_crop(ocplx *dst, int ndst, const ocplx *src, int nsrc, int nchan);
 void oracle_pad(ocplx *dst, int ndst, const ocplx *src, int nsrc, int nchan);
 void oracle_deapod(ocplx *a, int n, int nrep, float m, float sigma);
 void oracle_coilcombinesos(ocplx *img, const ocplx *coilimg, int nimg, int nchan);
+void oracle_coilcombinewalsh(ocplx *img, const ocplx *coilimg, int nimg, int nchan, int npatch);
 
 /* index-map dumps (bit-level comparison targets, see tests) */
 long oracle_grid_hits(int32_t *hits, long maxhits, int nxos, int nro, int npe,
@@ -82,6 +87,8 @@ long oracle_grid_hits(int32_t *hits, long maxhits, int nxos, int nro, int npe,
 
 /* one-slice pipelines (tron.cu:623-649 + 764) and the slice loop (tron.cu:726-786) */
 void oracle_nufft_adj_slice(const oracle_cfg *c, ocplx *img_out, const ocplx *samples, int peoffset);
+void oracle_nufft_adj_coils(const oracle_cfg *c, ocplx *coilimg_out, const ocplx *samples, int peoffset);
+void oracle_cgnr_coils(const oracle_cfg *c, ocplx *x, const ocplx *samples, int peoffset, int niter);
 void oracle_nufft_fwd_slice(const oracle_cfg *c, ocplx *samples_out, const ocplx *img);
 int  oracle_recon_radial2d(const oracle_cfg *c, ocplx *h_out, const ocplx *h_in);
 

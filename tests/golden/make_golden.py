@@ -14,12 +14,24 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle.oracle import RefLib  # noqa: E402
-from util import PARITY_CASES, case_input, synth_complex  # noqa: E402
+from util import PARITY_CASES, WALSH_CASES, case_input, synth_complex, walsh_input  # noqa: E402
 
 
-def main(outdir):
+def walsh_vectors(ref, outdir):
+    """coilcombinewalsh (tron.cu:270-302) alone: its call site (tron.cu:766) is commented out in the
+    reference, so the kernel is launched directly by the harness with the reference launch shape."""
+    out = {}
+    for nimg, nc, npatch in WALSH_CASES:
+        out["walsh_%d_%d_%d" % (nimg, nc, npatch)] = ref.walsh(walsh_input(nimg, nc), nimg, nc, npatch)
+    np.savez_compressed(os.path.join(outdir, "walsh.npz"), **out)
+    print("walsh ok", sorted(out))
+
+
+def main(outdir, only=None):
     os.makedirs(outdir, exist_ok=True)
     ref = RefLib()
+    if only == "walsh":
+        return walsh_vectors(ref, outdir)
     for name, (dims, flags) in sorted(PARITY_CASES.items()):
         ref.configure(dims, flags.get("adjoint", False), golden=flags.get("golden", False),
                       gridos=flags.get("gridos", 2.0), kernwidth=flags.get("kernwidth", 2.0),
@@ -52,7 +64,8 @@ def main(outdir):
     np.savez_compressed(os.path.join(outdir, "stages.npz"), grid_golden=g, grid_linear=gl,
                         degrid_golden=d, degrid_linear=dl, deapod_adj=da, deapod_fwd=df, **cs)
     print("stages ok")
+    walsh_vectors(ref, outdir)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden")
+    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden", sys.argv[2] if len(sys.argv) > 2 else None)

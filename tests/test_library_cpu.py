@@ -102,10 +102,14 @@ def test_geometry_rejections(lib):
         (dict(dims=[3, 1, 64, 64, 1], adjoint=True), "even"),                 # tron.cu:963
         (dict(dims=[2, 2, 64, 64, 1], adjoint=True), "nt"),
         (dict(dims=[1, 1, 64, 64, 2], adjoint=False), "dims\\[4\\]"),
-        (dict(dims=[1, 1, 64, 64, 1], adjoint=True, niter=3), "CGNR"),
+        (dict(dims=[1, 1, 64, 64, 1], adjoint=False, niter=3), "CGNR"),       # tron.cu:753-755: adjoint only
+        (dict(dims=[2, 1, 64, 64, 1], adjoint=True, niter=3, gridos=1.5), "CGNR"),   # needs nro == nxos
+        (dict(dims=[4, 1, 64, 64, 1], adjoint=True, niter=2, coils=(0, 2)), "coil shards"),
+        (dict(dims=[4, 1, 64, 64, 1], adjoint=True, coil_combine=1, per_coil_out=True), "Walsh"),
+        (dict(dims=[4, 1, 64, 64, 1], adjoint=True, coil_combine=2), "coil_combine"),
         (dict(dims=[1, 1, 64, 64, 1], adjoint=True, koosh=True), "koosh"),
     ]
-    for kw, pat in bad[:5]:
+    for kw, pat in bad:
         with pytest.raises(t.TronError, match=pat):
             t.geometry(t.make_config(**kw))
     with pytest.raises(t.TronError):

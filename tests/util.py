@@ -56,3 +56,20 @@ def case_input(name):
     stream = sorted(PARITY_CASES).index(name) + 1
     n = int(np.prod(dims))
     return synth_complex((n,), stream=stream)
+
+
+# coilcombinewalsh vectors (tests/golden/walsh.npz): (nimg, nc, npatch); nc <= 6 because the
+# reference zeroes NCHAN^2 = 36 matrix entries whatever nchan is (tron.cu:282)
+WALSH_CASES = [(32, 2, 1), (32, 4, 1), (32, 6, 1), (24, 6, 0), (24, 6, 2), (20, 4, 3)]
+
+
+def walsh_input(nimg, nc):
+    """Coil images with a smooth per-coil sensitivity on top of noise, (nimg, nimg, nc) complex64."""
+    z = synth_complex((nimg, nimg, nc), stream=200 + nc)
+    y, x = np.mgrid[0:nimg, 0:nimg].astype(np.float32) / nimg
+    obj = (1.0 + np.cos(3.0 * x) * np.sin(2.0 * y)).astype(np.float32)
+    out = np.empty_like(z)
+    for c in range(nc):
+        sens = np.exp(1j * (0.7 * c + 2.0 * x * (c + 1) / nc)) * (0.5 + (c + 1) / nc * y)
+        out[:, :, c] = (obj * sens + 0.2 * z[:, :, c]) * 1e-3
+    return np.ascontiguousarray(out.astype(np.complex64))

@@ -5,7 +5,9 @@ sm_100a) and the `tron` command line built from tron_b200/csrc; this package
 is the thin host-side binding used by the tests and bench.py.
 """
 from .api import (Config, Geometry, Plan, TronError, geometry, load_library, make_config, ra_read,
-                  ra_write, recon_radial2d, shard_slices, EXPORTED_SYMBOLS, LIB_PATH, CLI_PATH)
+                  ra_write, recon_radial2d, shard_slices, coilcombine_walsh_device, coilcombine_sos_device,
+                  EXPORTED_SYMBOLS, LIB_PATH, CLI_PATH)
 
 __all__ = ["Config", "Geometry", "Plan", "TronError", "geometry", "load_library", "make_config", "ra_read",
-           "ra_write", "recon_radial2d", "shard_slices", "EXPORTED_SYMBOLS", "LIB_PATH", "CLI_PATH"]
+           "ra_write", "recon_radial2d", "shard_slices", "coilcombine_walsh_device", "coilcombine_sos_device",
+           "EXPORTED_SYMBOLS", "LIB_PATH", "CLI_PATH"]

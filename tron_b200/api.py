@@ -35,7 +35,8 @@ class Config(C.Structure):
                 ("verbose", C.c_int), ("device", C.c_int),
                 ("half_in", C.c_int), ("half_out", C.c_int), ("slice_begin", C.c_int), ("slice_end", C.c_int),
                 ("coil_begin", C.c_int), ("coil_end", C.c_int), ("sos_partial", C.c_int),
-                ("batch_slices", C.c_int), ("per_coil_out", C.c_int)]
+                ("batch_slices", C.c_int), ("per_coil_out", C.c_int), ("coil_combine", C.c_int),
+                ("walsh_npatch", C.c_int)]
 
 
 class Geometry(C.Structure):
@@ -67,12 +68,13 @@ EXPORTED_SYMBOLS = [
     "tron_config_defaults", "tron_geometry_compute", "tron_plan_create", "tron_plan_destroy",
     "tron_plan_geometry", "tron_recon_host", "tron_recon_device", "tron_grid_device",
     "tron_grid_to_interleaved", "tron_degrid_device", "tron_plan_last_stage_ms", "tron_plan_last_launches",
-    "tron_plan_grid_debug",
+    "tron_plan_grid_debug", "tron_coilcombine_sos_device", "tron_coilcombine_walsh_device",
     "tron_last_error", "tron_version",
     # tron.h: legacy surface
     "tron_set_config", "tron_init", "tron_shutdown", "tron_nufft_adj_radial2d", "tron_nufft_radial2d",
     "recon_radial2d", "recon_radial_2d", "gridradial2d", "degridradial2d",
-    "tron_launch_gridradial2d", "tron_launch_degridradial2d",
+    "tron_launch_gridradial2d", "tron_launch_degridradial2d", "tron_cgnr_radial2d", "copy", "Caxpy",
+    "tron_launch_Caxpy",
     # ra.h
     "ra_read", "ra_write", "ra_free", "ra_query", "ra_reshape", "ra_convert", "ra_squash", "ra_diff",
     "ra_read_header", "ra_read_pinned", "ra_header_bytes",
@@ -103,6 +105,12 @@ def load_library(path=None):
     L.tron_grid_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.tron_grid_to_interleaved.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.tron_degrid_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tron_coilcombine_sos_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.tron_coilcombine_walsh_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.tron_launch_Caxpy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_size_t, C.c_int, C.c_int,
+                                    C.c_void_p]
+    L.tron_cgnr_radial2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.tron_cgnr_radial2d.restype = None
     L.tron_plan_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tron_plan_last_launches.argtypes = [C.c_void_p]
     L.tron_set_config.argtypes = [C.POINTER(Config)]
@@ -147,7 +155,8 @@ def _check(rc, lib):
 
 def make_config(dims, adjoint, golden=False, gridos=2.0, kernwidth=2.0, undersamp=1.0, prof_slide=0,
                 skip_angles=0, device=-1, half_in=False, half_out=False, slices=None, coils=None,
-                sos_partial=False, batch_slices=0, per_coil_out=False, niter=0, koosh=False):
+                sos_partial=False, batch_slices=0, per_coil_out=False, niter=0, koosh=False,
+                coil_combine=0, walsh_npatch=1):
     """The flags of the `tron` command line (tron.cu:822-874) as a tron_config."""
     lib = load_library()
     cfg = Config()
@@ -164,6 +173,7 @@ def make_config(dims, adjoint, golden=False, gridos=2.0, kernwidth=2.0, undersam
         cfg.coil_begin, cfg.coil_end = int(coils[0]), int(coils[1])
     cfg.sos_partial = int(bool(sos_partial)); cfg.batch_slices = int(batch_slices)
     cfg.per_coil_out = int(bool(per_coil_out)); cfg.niter = int(niter); cfg.koosh = int(bool(koosh))
+    cfg.coil_combine = int(coil_combine); cfg.walsh_npatch = int(walsh_npatch)
     return cfg
 
 
@@ -273,6 +283,20 @@ class Plan:
         ms = (C.c_float * 3)()
         _check(self.lib.tron_plan_last_stage_ms(self.handle, ms), self.lib)
         return [float(x) for x in ms]
+
+
+def coilcombine_walsh_device(d_img_ptr, d_coil_ptr, nimg, nchan, npatch=1, nslices=1, stream=0):
+    """coilcombinewalsh (tron.cu:270-302) on device pointers: [nslices][nimg][nimg][nchan] -> [nslices][nimg][nimg]."""
+    lib = load_library()
+    _check(lib.tron_coilcombine_walsh_device(C.c_void_p(d_img_ptr), C.c_void_p(d_coil_ptr), nimg, nchan, npatch,
+                                             nslices, C.c_void_p(stream)), lib)
+
+
+def coilcombine_sos_device(d_img_ptr, d_coil_ptr, nimg, nchan, nslices=1, stream=0):
+    """coilcombinesos (tron.cu:255-268) on device pointers."""
+    lib = load_library()
+    _check(lib.tron_coilcombine_sos_device(C.c_void_p(d_img_ptr), C.c_void_p(d_coil_ptr), nimg, nchan, nslices,
+                                           C.c_void_p(stream)), lib)
 
 
 def recon_radial2d(h_in, dims, **flags):

@@ -5,6 +5,7 @@
  *   gridradial2d, degridradial2d   __global__ kernels, callable with any <<<blocks,threads>>>
  *   tron_init, tron_shutdown, tron_nufft_adj_radial2d, tron_nufft_radial2d
  *   recon_radial2d (and the header's spelling recon_radial_2d)
+ *   tron_cgnr_radial2d, copy, Caxpy (tron.cu:651-720)
  *
  * In the reference these read file-static globals that only main() assigns
  * (tron.cu:54-87); tron_set_config() is the replacement for those assignments.
@@ -19,7 +20,7 @@ using namespace tronb;
 
 static tron_config g_cfg;
 static bool g_cfg_set = false;
-static tron_plan *g_adj = nullptr, *g_fwd = nullptr;
+static tron_plan *g_adj = nullptr, *g_fwd = nullptr, *g_cg = nullptr;
 
 static void die(const char *where)
 {
@@ -38,8 +39,8 @@ extern "C" int tron_set_config(const tron_config *cfg)
 
 extern "C" void tron_shutdown(void)
 {
-    tron_plan_destroy(g_adj); tron_plan_destroy(g_fwd);
-    g_adj = g_fwd = nullptr;
+    tron_plan_destroy(g_adj); tron_plan_destroy(g_fwd); tron_plan_destroy(g_cg);
+    g_adj = g_fwd = g_cg = nullptr;
 }
 
 /* tron.cu:579-606 allocates two stream slots; here one plan per direction owns
@@ -69,6 +70,52 @@ extern "C" void tron_nufft_radial2d(tron_float2 *d_out, tron_float2 *d_in, const
     if (!g_fwd) { set_error("tron_init() has not created a forward plan"); die("tron_nufft_radial2d"); }
     if (tron_recon_device(g_fwd, d_out, d_in, g_fwd->stream)) die("tron_nufft_radial2d");
     cudaStreamSynchronize(g_fwd->stream);
+}
+
+/* tron.cu:665-720: CGNR on the first window; per-coil images out, like the reference's d_p.
+ * The plan is kept between calls with the same iteration count. */
+extern "C" void tron_cgnr_radial2d(tron_float2 *d_out, tron_float2 *d_in, const int j, const int niter)
+{
+    (void)j;
+    if (!g_cfg_set) { set_error("tron_set_config() has not been called"); die("tron_cgnr_radial2d"); }
+    if (g_cg && g_cg->cfg.niter != niter) { tron_plan_destroy(g_cg); g_cg = nullptr; }
+    if (!g_cg) {
+        tron_config c = g_cfg;
+        c.adjoint = 1; c.niter = niter; c.slice_begin = 0; c.slice_end = 1; c.per_coil_out = 1; c.sos_partial = 0;
+        c.coil_combine = 0;
+        if (tron_plan_create(&g_cg, &c)) die("tron_cgnr_radial2d");
+    }
+    if (tron_recon_device(g_cg, d_out, d_in, g_cg->stream)) die("tron_cgnr_radial2d");
+    cudaStreamSynchronize(g_cg->stream);
+}
+
+/* tron.cu:651-655 */
+extern "C" void copy(tron_float2 *d_dst, tron_float2 *d_src, const size_t N, const int j)
+{
+    (void)j;
+    tron_plan *p = g_adj ? g_adj : (g_fwd ? g_fwd : g_cg);
+    cudaStream_t s = p ? p->stream : nullptr;
+    if (cudaMemcpyAsync(d_dst, d_src, N * sizeof(float2), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+        set_error("cudaMemcpyAsync failed"); die("copy");
+    }
+}
+
+/* tron.cu:658-663, same parameter list; size_t index so that N >= 2^31 works */
+extern "C" __global__ void Caxpy(float2 *d_z, float2 *d_y, float2 *d_x, float alpha, const size_t N)
+{
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < N; id += (size_t)blockDim.x * gridDim.x) {
+        const float2 y = d_y[id], x = d_x[id];
+        d_z[id] = make_float2(fmaf(alpha, x.x, y.x), fmaf(alpha, x.y, y.y));
+    }
+}
+
+extern "C" int tron_launch_Caxpy(void *d_z, const void *d_y, const void *d_x, float alpha, size_t N,
+                                 int blocks, int threads, void *stream)
+{
+    if (blocks < 1 || threads < 1 || threads > 1024) { set_error("bad launch configuration"); return TRON_EINVAL; }
+    Caxpy<<<blocks, threads, 0, (cudaStream_t)stream>>>((float2 *)d_z, (float2 *)d_y, (float2 *)d_x, alpha, N);
+    TRON_CUDA(cudaGetLastError());
+    return TRON_OK;
 }
 
 /* tron.cu:726-786: init, slice loop, shutdown -- here: plan, whole job, destroy */

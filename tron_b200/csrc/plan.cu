@@ -58,7 +58,10 @@ extern "C" void tron_config_defaults(tron_config *c)
 extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
 {
     memset(g, 0, sizeof *g);
-    if (c->niter != 0) { set_error("-i (CGNR) is not implemented; the reference marks it broken (tron.cu:670)"); return TRON_EUNSUPPORTED; }
+    if (c->niter < 0) { set_error("niter must be >= 0"); return TRON_EINVAL; }
+    if (c->niter > 0 && !c->adjoint) { set_error("-i (CGNR) applies to the adjoint direction only (tron.cu:753-755)"); return TRON_EINVAL; }
+    if (c->coil_combine != 0 && c->coil_combine != 1) { set_error("coil_combine must be 0 (sum of squares) or 1 (Walsh)"); return TRON_EINVAL; }
+    if (c->coil_combine == 1 && (c->walsh_npatch < 0 || c->walsh_npatch > 16)) { set_error("walsh_npatch must be in [0, 16]"); return TRON_EINVAL; }
     if (c->koosh) { set_error("-3 (koosh ball) has no kernels in the reference either"); return TRON_EUNSUPPORTED; }
     if (!(c->gridos > 0.f) || !(c->kernwidth > 0.f) || !(c->data_undersamp > 0.f)) { set_error("gridos, kernwidth and data_undersamp must be positive"); return TRON_EINVAL; }
     for (int i = 0; i < 5; ++i) if (c->dims[i] == 0 || c->dims[i] > 0x7fffffffULL) { set_error("dims[%d] = %llu out of range", i, (unsigned long long)c->dims[i]); return TRON_EINVAL; }
@@ -98,6 +101,9 @@ extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
     if (g->nt != 1) { set_error("nt = %d: the reference builds its FFT plans for nc channels but runs nc*nt (tron.cu:599-601); only nt = 1 is defined", g->nt); return TRON_EUNSUPPORTED; }
     if (g->nx < 1 || g->nxos < g->nx || (g->nxos & 1)) { set_error("nx = %d, nxos = %d: need an even oversampled grid >= nx", g->nx, g->nxos); return TRON_EINVAL; }
 
+    if (c->niter > 0 && g->nro != g->nxos) { set_error("-i (CGNR) needs nro == nxos (gridos 2): nro = %d, nxos = %d", g->nro, g->nxos); return TRON_EUNSUPPORTED; }
+    if (c->adjoint && c->coil_combine == 1 && g->nc > 1 && (c->per_coil_out || c->sos_partial)) { set_error("the Walsh combine excludes per_coil_out and sos_partial"); return TRON_EINVAL; }
+
     g->slice_begin = c->slice_begin; g->slice_end = c->slice_end;
     if (g->slice_begin == 0 && g->slice_end == 0) g->slice_end = c->adjoint ? g->nz : 1;
     if (!c->adjoint) { g->slice_begin = 0; g->slice_end = 1; }
@@ -106,6 +112,7 @@ extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
     if (g->coil_begin == 0 && g->coil_end == 0) g->coil_end = g->nc;
     if (g->coil_begin < 0 || g->coil_end > g->nc || g->coil_begin >= g->coil_end) { set_error("bad coil shard [%d,%d) of %d", g->coil_begin, g->coil_end, g->nc); return TRON_EINVAL; }
     int nch = g->coil_end - g->coil_begin;
+    if (nch != g->nc && c->adjoint && (c->niter > 0 || c->coil_combine == 1)) { set_error("CGNR and the Walsh combine need every coil of a slice: coil shards are not supported"); return TRON_EUNSUPPORTED; }
     if (g->nc > 1 && ((g->coil_begin & 1) || (nch & 1))) { set_error("coil shards must start at an even channel and hold an even count"); return TRON_EINVAL; }
 
     uint64_t spoke = (uint64_t)g->nc * g->nt * g->nro;
@@ -130,6 +137,7 @@ static void plan_release(tron_plan *p)
     fft_plan_free(p->fft);
     cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->heavy_cells); cudaFree(p->grid_dbg);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_gridi); cudaFree(p->d_in); cudaFree(p->d_out);
+    cudaFree(p->d_coil); cudaFree(p->cg_r); cudaFree(p->cg_v); cudaFree(p->cg_z); cudaFree(p->cg_p); cudaFree(p->cg_part);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_in) cudaStreamDestroy(p->copy_in);
     if (p->copy_out) cudaStreamDestroy(p->copy_out);
@@ -149,6 +157,8 @@ static int pick_batch(const tron_plan *p)
     const char *e = getenv("TRON_BATCH");
     if (e && atoi(e) > 0) return atoi(e) < p->nslices ? atoi(e) : p->nslices;
     size_t per = (size_t)p->nch * p->g.nxos * ((size_t)p->g.nxos + p->g.nx) * sizeof(float2);
+    if (p->percoil) per += (size_t)p->g.nc * p->g.nx * p->g.nx * sizeof(float2);
+    if (p->cfg.niter > 0) per += 2 * (size_t)p->g.nc * ((size_t)p->g.nx * p->g.nx + (size_t)p->g.nro * p->g.npe1work) * sizeof(float2);
     /* launches of >= 32 slices reach the kernels' asymptotic throughput (profiles/r01_grid_only_timing.txt);
      * the work buffers are bounded to ~1.5 GB of the 180 GB */
     size_t b = ((size_t)1536 << 20) / (per ? per : 1);
@@ -180,6 +190,8 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     p->nch = g.coil_end - g.coil_begin;
     p->nslices = g.slice_end - g.slice_begin;
     p->kb = make_kb(cfg->kernwidth);              /* plan-time polynomial fit, refmath.cuh */
+    /* paths that need every coil image of a slice at once (combine.cu, cgnr.cu) */
+    p->percoil = cfg->adjoint && (cfg->niter > 0 || (cfg->coil_combine == 1 && g.nc > 1));
     p->in_elem_bytes = cfg->half_in ? 4 : 8;
     p->out_elem_bytes = cfg->half_out ? 4 : 8;
     if (cfg->adjoint && cfg->sos_partial && g.nc > 1) p->out_elem_bytes = 4;
@@ -215,6 +227,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         if (cfg->golden_angle && p->nslices > 1 && 2 * g.prof_slide <= g.npe1work) gs = 4;
         const char *eg = getenv("TRON_GROUP");
         if (eg && cfg->golden_angle && (atoi(eg) == 1 || atoi(eg) == 4)) gs = atoi(eg);
+        if (cfg->niter > 0) gs = 1;                       /* residuals of overlapping windows are not shared */
         int nun = (gs - 1) * g.prof_slide + g.npe1work;                 /* union window of a group */
         int ntab = cfg->golden_angle ? (p->nslices + gs - 1) / gs : 1;
         int skip = cfg->skip_angles + (cfg->golden_angle ? g.slice_begin * g.prof_slide : 0);
@@ -243,11 +256,22 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         PLAN_CUDA(cudaMalloc(&p->grid_dbg, (size_t)8 * 65536 * 8 * sizeof(long long)));
         PLAN_CUDA(cudaMemset(p->grid_dbg, 0, (size_t)8 * 65536 * 8 * sizeof(long long)));
     }
-    p->overlap = cfg->adjoint && p->nslices > p->batch && getenv("TRON_OVERLAP") != nullptr;   /* measured slower on B200: off */
+    p->overlap = cfg->adjoint && !p->percoil && p->nslices > p->batch && getenv("TRON_OVERLAP") != nullptr;   /* measured slower on B200: off */
     PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)(p->overlap ? 2 : 1) * p->batch * p->nch * n * n * sizeof(float2)));
     PLAN_CUDA(cudaMalloc(&p->d_tmp, (size_t)p->batch * p->nch * n * g.nx * sizeof(float2)));
     if (!cfg->adjoint && p->nch >= 32 && p->nch % 32 == 0)
         PLAN_CUDA(cudaMalloc(&p->d_gridi, (size_t)p->nch * n * n * sizeof(float2)));
+    if (p->percoil) {
+        const size_t N = (size_t)p->batch * g.nc * g.nx * g.nx, ns = (size_t)p->batch * g.nc * g.nro * g.npe1work;
+        PLAN_CUDA(cudaMalloc(&p->d_coil, N * sizeof(float2)));
+        if (cfg->niter > 0) {
+            PLAN_CUDA(cudaMalloc(&p->cg_z, N * sizeof(float2)));
+            PLAN_CUDA(cudaMalloc(&p->cg_p, N * sizeof(float2)));
+            PLAN_CUDA(cudaMalloc(&p->cg_r, ns * sizeof(float2)));
+            PLAN_CUDA(cudaMalloc(&p->cg_v, ns * sizeof(float2)));
+            PLAN_CUDA(cudaMalloc(&p->cg_part, cg_part_doubles(p->batch) * sizeof(double)));
+        }
+    }
     PLAN_CUDA(cudaStreamSynchronize(p->stream));
 #undef PLAN_TRY
 #undef PLAN_CUDA
@@ -271,7 +295,8 @@ extern "C" int tron_plan_geometry(const tron_plan *p, tron_geometry *g)
     return TRON_OK;
 }
 
-static GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d_grid, int z0, int nb)
+namespace tronb {
+GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d_grid, int z0, int nb)
 {
     const tron_geometry &g = p->g;
     GridLaunch L;
@@ -294,6 +319,7 @@ static GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, fl
     L.dbg = p->grid_dbg;
     return L;
 }
+} // namespace tronb
 
 static int adjoint_mode(const tron_plan *p)
 {
@@ -321,6 +347,22 @@ static int launch_batch_fft(tron_plan *p, void *d_out, const float2 *d_grid, int
     a.out = (char *)d_out + (size_t)z0 * per * p->out_elem_bytes;
     p->last_launches += 2;
     return launch_adj_fft(p->fft, a, s);
+}
+
+/* One batch through the per-coil path: per-coil images (plain adjoint or CGNR, cgnr.cu), then the
+ * coil combine the configuration asks for (combine.cu). */
+static int launch_batch_percoil(tron_plan *p, void *d_out, const void *d_in, int z0, int nb, cudaStream_t s)
+{
+    const tron_geometry &g = p->g;
+    int rc = run_percoil_batch(p, d_in, z0, nb, s);
+    if (rc) return rc;
+    const int mode = adjoint_mode(p);
+    const size_t per = (size_t)g.nx * g.ny * (mode == 2 ? (size_t)g.nc : 1);
+    void *out = (char *)d_out + (size_t)z0 * per * p->out_elem_bytes;
+    p->last_launches += 1;
+    if (p->cfg.coil_combine == 1 && g.nc > 1)
+        return launch_walsh(out, p->d_coil, g.nx, g.nc, p->cfg.walsh_npatch, nb, p->cfg.half_out, s);
+    return launch_coil_combine(out, p->d_coil, (size_t)nb * g.nx * g.ny, g.nc, mode, p->cfg.half_out, s);
 }
 
 /* All adjoint slices of the plan.  Gridding (instruction-issue bound) runs on a low-priority
@@ -374,15 +416,18 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
         }
         if (overlap) TRON_CUDA(cudaStreamWaitEvent(sg, p->ev_fft[i], 0));   /* buffer i free again */
         if (p->stage_timing) cudaEventRecord(p->ev_t[0], sg);
-        int rc = launch_batch_grid(p, d_in, gridbuf, z0, nb, sg);
+        int rc = p->percoil ? launch_batch_percoil(p, d_out, d_in, z0, nb, sg)
+                            : launch_batch_grid(p, d_in, gridbuf, z0, nb, sg);
         if (rc) return rc;
         if (p->stage_timing) cudaEventRecord(p->ev_t[1], sg);
         if (overlap) {
             TRON_CUDA(cudaEventRecord(p->ev_grid[i], sg));
             TRON_CUDA(cudaStreamWaitEvent(sf, p->ev_grid[i], 0));
         }
-        rc = launch_batch_fft(p, d_out, gridbuf, z0, nb, sf);
-        if (rc) return rc;
+        if (!p->percoil) {
+            rc = launch_batch_fft(p, d_out, gridbuf, z0, nb, sf);
+            if (rc) return rc;
+        }
         if (p->stage_timing) {                     /* diagnostic mode: serialises host and device */
             cudaEventRecord(p->ev_t[2], sf);
             cudaEventSynchronize(p->ev_t[2]);

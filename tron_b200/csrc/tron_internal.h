@@ -108,7 +108,20 @@ struct FwdFftLaunch {
 int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s);
 int launch_deapod_tables(float *adj_tab, float *fwd_tab, int nx, int nxos, float W, float gridos, cudaStream_t s);
 
+/* coil combination of channel-interleaved per-coil images (combine.cu) */
+int launch_coil_combine(void *out, const float2 *coil, size_t npix, int nc, int mode, int half_out, cudaStream_t s);
+int launch_walsh(void *out, const float2 *coil, int nimg, int nc, int npatch, int nslices, int half_out, cudaStream_t s);
+
 } // namespace tronb
+
+struct tron_plan;
+namespace tronb {
+/* plan.cu */
+GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d_grid, int z0, int nb);
+/* cgnr.cu: per-coil images of slices [z0, z0 + nb) into plan->d_coil (plain adjoint or CGNR) */
+int run_percoil_batch(tron_plan *p, const void *d_in, int z0, int nb, cudaStream_t s);
+size_t cg_part_doubles(int batch);
+}
 
 struct tron_plan {
     tron_config cfg;
@@ -117,6 +130,7 @@ struct tron_plan {
     int nch = 0;                         /* channels this plan owns */
     int nslices = 0;                     /* slices this plan owns */
     int batch = 1;
+    int percoil = 0;                     /* adjoint through per-coil images: Walsh combine and/or CGNR */
     cudaStream_t stream = nullptr;       /* compute */
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaStream_t s_grid = nullptr, s_fft = nullptr;   /* low / high priority compute streams */
@@ -132,6 +146,10 @@ struct tron_plan {
     int nheavy = 0, heavy_r2 = -1;
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
     float2 *d_gridi = nullptr;                      /* forward, nc >= 32: channel-interleaved copy of the grid */
+    float2 *d_coil = nullptr;                       /* per-coil images of a batch (Walsh combine, CGNR iterate x) */
+    float2 *cg_r = nullptr, *cg_v = nullptr;        /* CGNR: residual and A p, [batch][npe1work][nro][nc] */
+    float2 *cg_z = nullptr, *cg_p = nullptr;        /* CGNR: B r and search direction, [batch][nx][nx][nc] */
+    double *cg_part = nullptr;                      /* CGNR: partial inner products */
     void *d_in = nullptr, *d_out = nullptr;         /* device staging for the host API */
     size_t in_bytes = 0, out_bytes = 0;
     size_t in_elem_bytes = 8, out_elem_bytes = 8;

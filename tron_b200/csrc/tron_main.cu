@@ -15,6 +15,9 @@
  * Additions, none of which change an existing letter:
  *   -H   write the output with half-precision elements (fp16 storage);
  *        a half-precision input (eltype 4 / elbyte 4) is detected from the header.
+ *   -w npatch  adaptive (Walsh) coil combine with a (2 npatch + 1)^2 patch instead of the root
+ *        sum of squares: the call the reference keeps commented out at tron.cu:766 (npatch 1).
+ *   -i niter   runs the CGNR iteration of cgnr.cu (the reference's own is self-declared broken).
  *   -v   additionally prints one machine-readable JSON timing line.
  */
 #include <getopt.h>
@@ -31,7 +34,7 @@ static void print_usage(void)
 {
     fprintf(stderr, "Trajectory-optimized Non-uniform Fast Fourier Transform (B200 engine)\n");
     fprintf(stderr, "Usage: tron [-3aGhHv] [-B blocks] [-d prof_slide] [-g gpu] [-i niter] [-k width] [-o gridos] "
-                    "[-r nro] [-s skip_angles] [-T threads] [-u data_undersamp] <infile.ra> [outfile.ra]\n");
+                    "[-r nro] [-s skip_angles] [-T threads] [-u data_undersamp] [-w npatch] <infile.ra> [outfile.ra]\n");
     fprintf(stderr, "\t-3\t\t\t3D koosh ball trajectory (not implemented)\n");
     fprintf(stderr, "\t-a\t\t\tadjoint operation\n");
     fprintf(stderr, "\t-B blocks\t\tnumber of GPU blocks (ignored)\n");
@@ -48,6 +51,7 @@ static void print_usage(void)
     fprintf(stderr, "\t-T threads\t\tnumber of GPU threads (ignored)\n");
     fprintf(stderr, "\t-u data_undersamp\tinput data undersampling factor\n");
     fprintf(stderr, "\t-v\t\t\tverbose output\n");
+    fprintf(stderr, "\t-w npatch\t\tadaptive (Walsh) coil combine, patch half-width npatch\n");
 }
 
 static double now_s(void)
@@ -62,7 +66,7 @@ int main(int argc, char *argv[])
     tron_config_defaults(&cfg);
     int c;
     opterr = 0;
-    while ((c = getopt(argc, argv, "3aB:d:g:Ghi:k:o:r:s:T:u:vH")) != -1) {
+    while ((c = getopt(argc, argv, "3aB:d:g:Ghi:k:o:r:s:T:u:vHw:")) != -1) {
         switch (c) {
         case '3': cfg.koosh = 1; break;
         case 'a': cfg.adjoint = 1; break;
@@ -80,6 +84,7 @@ int main(int argc, char *argv[])
         case 's': cfg.skip_angles = atoi(optarg); break;
         case 'T': break;
         case 'v': cfg.verbose = 1; break;
+        case 'w': cfg.coil_combine = 1; cfg.walsh_npatch = atoi(optarg); break;
         default: print_usage(); return 1;
         }
     }
