@@ -158,3 +158,85 @@ def test_oracle_adjoint_linearity_and_window(oracle):
     out2 = oracle.recon(cfg, x2.ravel()).reshape(cfg.nz, cfg.nx, cfg.nx)
     assert not np.array_equal(out[0], out2[0]) and not np.array_equal(out[1], out2[1])
     assert np.array_equal(out[2:], out2[2:])
+
+
+# ---------------------------------------------------------------- Walsh combine, CGNR
+def test_oracle_walsh_matches_reference_golden(oracle):
+    """coilcombinewalsh (tron.cu:270-302) run by oracle/_ref on a B200 -> tests/golden/walsh.npz."""
+    from util import WALSH_CASES, walsh_input
+    gold = np.load(os.path.join(GOLD, "walsh.npz"))
+    for nimg, nc, npatch in WALSH_CASES:
+        got = oracle.walsh(walsh_input(nimg, nc), nimg, nc, npatch)
+        want = gold["walsh_%d_%d_%d" % (nimg, nc, npatch)]
+        assert rel_l2(got, want) <= 1e-5, (nimg, nc, npatch, rel_l2(got, want))
+
+
+def test_oracle_walsh_properties(oracle):
+    one = synth_complex((12, 12, 1), stream=301)
+    assert np.array_equal(oracle.walsh(one, 12, 1, 1), one[:, :, 0])            # tron.cu:277-278
+    # rank-one coil images z_c = s_c m: the dominant eigenvector is s/|s| up to the phase of s^H 1,
+    # so out = (1^T s)/|1^T s| |s| m
+    nimg, nc = 16, 4
+    m = synth_complex((nimg, nimg), stream=302)
+    s = (np.array([1.0, 0.5j, -0.7, 0.2 + 0.3j])).astype(np.complex64)
+    z = (m[:, :, None] * s[None, None, :]).astype(np.complex64)
+    out = oracle.walsh(z, nimg, nc, 1)
+    ph = s.sum() / abs(s.sum())
+    assert rel_l2(out, ph * np.linalg.norm(s) * m) <= 1e-5
+    # npatch = 0 is the pixel's own outer product: |out| is the root sum of squares
+    z = synth_complex((nimg, nimg, 6), stream=303)
+    assert rel_l2(np.abs(oracle.walsh(z, nimg, 6, 0)), np.abs(oracle.sos(z, nimg, 6))) <= 1e-5
+
+
+def test_oracle_walsh_in_the_slice_loop(oracle):
+    dims, flags = PARITY_CASES["P2_slide"]
+    x = case_input("P2_slide")
+    cfg = oracle.config(dims, True, golden=True, undersamp=0.25, prof_slide=7, skip_angles=3,
+                        coil_combine=1, walsh_npatch=1)
+    out = oracle.recon(cfg, x).reshape(cfg.nz, cfg.nx, cfg.nx)
+    coils = oracle.adj_coils(cfg, x[cfg.nc * cfg.nro * 7 * 2:], peoffset=14)      # slice 2
+    assert np.array_equal(out[2], oracle.walsh(coils, cfg.nx, cfg.nc, 1))
+
+
+def _cg_phantom(oracle, nc, nx, npe):
+    import ctypes as C
+    from oracle.oracle import _Cfg, _ptr
+    y, x = (np.mgrid[0:nx, 0:nx] - nx / 2).astype(np.float32)
+    obj = ((x ** 2 + y ** 2) < (0.36 * nx) ** 2).astype(np.float32) + 0.5 * (((x - 4) ** 2 + (y + 3) ** 2) < 16)
+    truth = np.zeros((nx, nx, nc), dtype=np.complex64)
+    for c in range(nc):
+        truth[:, :, c] = obj * np.exp(1j * 0.3 * c * x / nx) * (1 + 0.2 * c)
+    fcfg = oracle.config([nc, 1, nx, nx, 1], False, golden=True)
+    full = np.zeros((fcfg.npe1work, fcfg.nro, nc), dtype=np.complex64)
+    oracle.lib.oracle_nufft_fwd_slice.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_void_p]
+    oracle.lib.oracle_nufft_fwd_slice(C.byref(fcfg), _ptr(full), _ptr(truth))
+    return truth, np.ascontiguousarray(full[:npe])
+
+
+def test_oracle_cgnr_converges(oracle):
+    """The repaired CGNR (see oracle_cgnr_coils) reduces the error against the phantom monotonically
+    over 16 iterations; one iteration is the adjoint image times the optimal step."""
+    nc, nx, npe = 2, 32, 64
+    truth, samples = _cg_phantom(oracle, nc, nx, npe)
+    cfg = oracle.config([nc, 1, 2 * nx, npe, 1], True, golden=True)
+    errs = [rel_l2(oracle.cgnr_coils(cfg, samples, 0, it), truth) for it in (1, 2, 4, 8, 16)]
+    assert all(b < a for a, b in zip(errs, errs[1:])), errs
+    assert errs[-1] < 0.08, errs
+    x1 = oracle.cgnr_coils(cfg, samples, 0, 1)
+    adj = oracle.adj_coils(cfg, samples)
+    inner = (slice(1, None), slice(1, None))          # row 0 / column 0 are cleared (pad drops them)
+    ratio = x1[inner] / adj[inner]
+    # B uses the forward model's deapodisation table, the plain adjoint its own (F9 quirk): the
+    # two differ by a smooth real factor close to a constant
+    assert np.std(np.abs(ratio)) / np.mean(np.abs(ratio)) < 0.05
+    assert np.all(x1[0] == 0) and np.all(x1[:, 0] == 0)
+
+
+def test_oracle_cgnr_in_the_slice_loop(oracle):
+    dims = [2, 1, 32, 40, 1]
+    x = synth_complex((int(np.prod(dims)),), stream=304)
+    cfg = oracle.config(dims, True, golden=True, undersamp=0.5, prof_slide=8, skip_angles=1, niter=2)
+    out = oracle.recon(cfg, x).reshape(cfg.nz, cfg.nx, cfg.nx)
+    z = 2
+    coils = oracle.cgnr_coils(cfg, x[cfg.nc * cfg.nro * 8 * z:], peoffset=8 * z, niter=2)
+    assert np.array_equal(out[z], oracle.sos(coils, cfg.nx, cfg.nc))
