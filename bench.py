@@ -48,6 +48,12 @@ WORKLOADS = {
              "BASELINE cfg3 per-GPU shard: dims [32,1,512,25728,1], -a -G -u 1.5703125 -d 804, 32 slices of 256x256"),
     "cfg4": ([16, 1, 256, 128 + 21 * 249, 1], dict(adjoint=True, golden=True, undersamp=0.5, prof_slide=21),
              "BASELINE cfg4 per-GPU shard: dims [16,1,256,5357,1], -u 0.5 -d 21 -a -G, 250 frames of 128x128"),
+    # SURVEY 8(f) rows N4 / N3 on the cfg2 acquisition (not driver-run; profiles/ holds their lines)
+    "cfg2_walsh": ([6, 1, 512, 20271, 1], dict(adjoint=True, golden=True, undersamp=0.4, prof_slide=21,
+                                               coil_combine=1, walsh_npatch=1),
+                   "cfg2 acquisition, -a -G -u 0.4 -d 21 -w 1: adaptive (Walsh) coil combine instead of RSS"),
+    "cfg2_cgnr3": ([6, 1, 512, 20271, 1], dict(adjoint=True, golden=True, undersamp=0.4, prof_slide=21, niter=3),
+                   "cfg2 acquisition, -a -G -u 0.4 -d 21 -i 3: three CGNR iterations per slice, coil RSS"),
     "small": ([6, 1, 512, 204 + 21 * 15, 1], dict(adjoint=True, golden=True, undersamp=0.4, prof_slide=21),
               "16-slice stretch of cfg2 (smoke)"),
 }

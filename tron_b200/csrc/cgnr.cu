@@ -208,22 +208,24 @@ int run_percoil_batch(tron_plan *p, const void *d_in, int z0, int nb, cudaStream
     TRON_CUDA(cudaGetLastError());
     p->last_launches += 3;
     for (int t = 0; t < niter; ++t) {
-        for (int b = 0; b < nb; ++b) {                   /* v_b = A p_b */
+        {                                                /* v_b = A p_b, the whole batch per launch */
             FwdFftLaunch f;
-            f.img = p->cg_p + (size_t)b * N; f.tmp = p->d_tmp; f.grid = p->d_grid; f.deapod = p->deapod_fwd;
-            f.nch = p->nch; f.nc_total = nc; f.ch0 = g.coil_begin; f.half_in = 0;
+            f.img = p->cg_p; f.tmp = p->d_tmp; f.grid = p->d_grid; f.deapod = p->deapod_fwd;
+            f.nch = p->nch; f.nc_total = nc; f.ch0 = g.coil_begin; f.half_in = 0; f.nimg = nb;
             rc = launch_fwd_fft(p->fft, f, s);
             if (rc) return rc;
             DegridLaunch d;
-            const int tabi = p->tabs.ntab > 1 ? z0 + b : 0;
-            d.samples = p->cg_v + (size_t)b * n; d.grid = p->d_grid; d.cs = p->tabs.cs_lin + (size_t)tabi * p->tabs.npe;
+            const int per_slice = p->tabs.ntab > 1;
+            d.samples = p->cg_v; d.grid = p->d_grid;
+            d.cs = p->tabs.cs_lin + (size_t)(per_slice ? z0 : 0) * p->tabs.npe;
+            d.cs_stride = per_slice ? p->tabs.npe : 0;
             d.n = g.nxos; d.nro = g.nro; d.npe = g.npe1work;
             d.nc_total = nc; d.ch0 = g.coil_begin; d.nch = p->nch;
-            d.kb = p->kb; d.half_out = 0;
+            d.kb = p->kb; d.half_out = 0; d.nimg = nb;
             rc = launch_degrid(d, s);
             if (rc) return rc;
         }
-        p->last_launches += 3 * nb;
+        p->last_launches += 3;
         const int last = t == niter - 1;
         cg_vwv_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_v, part_vwv, n, g.nro, nc, wa, wb);
         cg_step_kernel<<<gr, CG_THREADS, 0, s>>>(x, p->cg_p, p->cg_r, p->cg_v, part_zz[t & 1], part_vwv, N, n,

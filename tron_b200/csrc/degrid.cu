@@ -56,6 +56,10 @@ degrid_gather_kernel(const DegridLaunch d)
     const float c0 = (float)((n + 1) / 2);
     const float inv_nro = rcp_approx((float)d.nro);
     const size_t plane = (size_t)n * n;
+    /* blockIdx.y = grid of a batch (CGNR): its own plane set, spoke table and sample block */
+    const float2 *grid_b = d.grid + (size_t)blockIdx.y * d.nch * plane;
+    const float2 *cs_b = d.cs + (size_t)blockIdx.y * d.cs_stride;
+    const size_t samp_b = (size_t)blockIdx.y * nsamp * d.nc_total;
 
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (size_t)gridDim.x * blockDim.x) {
@@ -64,7 +68,7 @@ degrid_gather_kernel(const DegridLaunch d)
         const int chunk = (int)(t / nsamp);
         const size_t id = t - (size_t)chunk * nsamp;
         const int pe = (int)(id / d.nro), ro = (int)(id - (size_t)pe * d.nro);
-        const float2 cs = __ldg(d.cs + pe);
+        const float2 cs = __ldg(cs_b + pe);
         const float R = fma_ftz((float)ro, inv_nro, -0.5f);
         const float nR = mul_ftz(R, (float)n);
         const float X = fma_ftz(cs.y, nR, c0);          /* rows:    sin */
@@ -87,7 +91,7 @@ degrid_gather_kernel(const DegridLaunch d)
         float2 acc[CH];
 #pragma unroll
         for (int i = 0; i < CH; ++i) acc[i] = make_float2(0.f, 0.f);
-        const float2 *g0 = d.grid + (size_t)chunk * CH * plane;
+        const float2 *g0 = grid_b + (size_t)chunk * CH * plane;
 
         const float xtop = X + W;
         for (int xu = (int)ceilf(X - W); (float)xu <= xtop; ++xu) {
@@ -108,7 +112,7 @@ degrid_gather_kernel(const DegridLaunch d)
                 }
             }
         }
-        store_sample<CH, HALF>(d.samples, id * d.nc_total + d.ch0 + (size_t)chunk * CH, acc);
+        store_sample<CH, HALF>(d.samples, samp_b + id * d.nc_total + d.ch0 + (size_t)chunk * CH, acc);
     }
 }
 
@@ -116,8 +120,9 @@ template <int CH, int NT>
 static int launch_degrid_nt(const DegridLaunch &d, cudaStream_t s)
 {
     size_t total = (size_t)d.nro * d.npe * (d.nch / CH);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 64) blocks = 148 * 64;
+    int bx = (int)((total + 255) / 256);
+    if (bx > 148 * 64) bx = 148 * 64;
+    dim3 blocks(bx, d.nimg > 0 ? d.nimg : 1);
     if (d.half_out) degrid_gather_kernel<CH, true, NT><<<blocks, 256, 0, s>>>(d);
     else            degrid_gather_kernel<CH, false, NT><<<blocks, 256, 0, s>>>(d);
     TRON_CUDA(cudaGetLastError());

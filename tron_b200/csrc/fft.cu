@@ -283,13 +283,14 @@ adj_pass_b_kernel(const float2 *__restrict__ tmp, void *__restrict__ outv, const
 /* ------- forward pass A: pad + deapodise on load, FFT along columns ------- */
 __global__ void __launch_bounds__(256)
 fwd_pass_a_kernel(const void *__restrict__ imgv, float2 *__restrict__ tmp, const float *__restrict__ deapod,
-                  const float2 *__restrict__ tw, const PassGeom p, int nc_total, int ch0, int half_in)
+                  const float2 *__restrict__ tw, const PassGeom p, int nch, int nc_total, int ch0, int half_in)
 {
     extern __shared__ float2 smem[];
     const int n = p.n, L = p.L, pitch = p.pitch, nx = p.nkeep;
     float2 *bufA = smem, *bufB = smem + L * pitch, *stw = smem + 2 * L * pitch;
     const int a0 = blockIdx.x * L;
-    const int ch = blockIdx.y;
+    const int ch = blockIdx.y % nch;                     /* blockIdx.y = image * nch + channel */
+    const size_t img0 = (size_t)(blockIdx.y / nch) * nx * nx * nc_total;
     const int w = (n - nx) / 2, h = n / 2;
     load_twiddles(stw, tw, n);
     for (int idx = threadIdx.x; idx < L * pitch; idx += blockDim.x) bufA[idx] = make_float2(0.f, 0.f);
@@ -298,7 +299,7 @@ fwd_pass_a_kernel(const void *__restrict__ imgv, float2 *__restrict__ tmp, const
         int l = idx / nx, b = idx - l * nx, a = a0 + l;
         /* pad drops source row 0 and column 0 (tron.cu:449-450) */
         if (a >= 1 && a < nx && b >= 1) {
-            size_t e = ((size_t)a * nx + b) * nc_total + ch0 + ch;
+            size_t e = img0 + ((size_t)a * nx + b) * nc_total + ch0 + ch;
             float2 v = half_in ? __half22float2(((const __half2 *)imgv)[e]) : ((const float2 *)imgv)[e];
             float s = __ldg(deapod + (size_t)a * nx + b);
             bufA[l * pitch + phys(b + w)] = make_float2(v.x * s, v.y * s);
@@ -306,7 +307,7 @@ fwd_pass_a_kernel(const void *__restrict__ imgv, float2 *__restrict__ tmp, const
     }
     __syncthreads();
     float2 *res = fft_lines(bufA, bufB, stw, n, L, pitch, p.f, -1.f);
-    float2 *out = tmp + (size_t)ch * n * nx + a0;
+    float2 *out = tmp + (size_t)blockIdx.y * n * nx + a0;
     for (int idx = threadIdx.x; idx < n * L; idx += blockDim.x) {
         int c = idx / L, l = idx - c * L;
         int k = c + h; if (k >= n) k -= n;
@@ -556,14 +557,15 @@ p2_adj_pass_b(const float2 *__restrict__ tmp, void *__restrict__ outv, const flo
 template <int N, int L>
 __global__ void __launch_bounds__(L *(N / 8))
 p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const float *__restrict__ deapod,
-              const float2 *__restrict__ tw, int nx, int nc_total, int ch0, int half_in)
+              const float2 *__restrict__ tw, int nx, int nch, int nc_total, int ch0, int half_in)
 {
     extern __shared__ float2 smem[];
     constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
     float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
     const int l = threadIdx.x / T, j = threadIdx.x % T;
     const int a = blockIdx.x * L + l;
-    const int ch = blockIdx.y;
+    const int ch = blockIdx.y % nch;                 /* blockIdx.y = image * nch + channel */
+    const size_t img0 = (size_t)(blockIdx.y / nch) * nx * nx * nc_total;
     const int w = (N - nx) / 2, h = N / 2;
     for (int i = threadIdx.x; i < N; i += L * T) stw[phys(i)] = tw[i];
     float2 v[8];
@@ -572,7 +574,7 @@ p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const flo
         const int b = j + q * T - w;                 /* source column of padded column j + q*T */
         v[q] = make_float2(0.f, 0.f);
         if (a >= 1 && a < nx && b >= 1 && b < nx) {  /* pad drops row 0 and column 0, tron.cu:449-450 */
-            const size_t e = ((size_t)a * nx + b) * nc_total + ch0 + ch;
+            const size_t e = img0 + ((size_t)a * nx + b) * nc_total + ch0 + ch;
             float2 x = half_in ? __half22float2(((const __half2 *)imgv)[e]) : ((const float2 *)imgv)[e];
             const float s = __ldg(deapod + (size_t)a * nx + b);
             v[q] = make_float2(x.x * s, x.y * s);
@@ -581,7 +583,7 @@ p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const flo
     __syncthreads();
     float2 *res = p2_fft<N, -1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j, l) - l * PITCH;
     const int a0 = blockIdx.x * L;
-    float2 *out = tmp + (size_t)ch * N * nx + a0;
+    float2 *out = tmp + (size_t)blockIdx.y * N * nx + a0;
     for (int idx = threadIdx.x; idx < N * L; idx += L * T) {
         const int c = idx / L, ll = idx % L;
         const int k = (c + h) & (N - 1);
@@ -910,10 +912,11 @@ template <int N, int L> struct P2Launch {
     }
     static int fwd(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)
     {
-        dim3 ga((f.nkeep + L - 1) / L, a.nch);
-        p2_fwd_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.img, a.tmp, a.deapod, f.tw, f.nkeep, a.nc_total, a.ch0, a.half_in);
+        const int nimg = a.nimg > 0 ? a.nimg : 1;
+        dim3 ga((f.nkeep + L - 1) / L, a.nch * nimg);
+        p2_fwd_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.img, a.tmp, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total, a.ch0, a.half_in);
         TRON_CUDA(cudaGetLastError());
-        dim3 gb(N / L, a.nch);
+        dim3 gb(N / L, a.nch * nimg);
         p2_fwd_pass_b<N, L><<<gb, THREADS, SMEM, s>>>(a.tmp, a.grid, f.tw, f.nkeep);
         TRON_CUDA(cudaGetLastError());
         return 0;
@@ -1055,10 +1058,11 @@ int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)
 {
     if (f.pow2) return p2_fwd(f, a, s);
     PassGeom p = make_geom(f);
-    dim3 ga((f.nkeep + p.L - 1) / p.L, a.nch);
-    fwd_pass_a_kernel<<<ga, 256, f.smem, s>>>(a.img, a.tmp, a.deapod, f.tw, p, a.nc_total, a.ch0, a.half_in);
+    const int nimg = a.nimg > 0 ? a.nimg : 1;
+    dim3 ga((f.nkeep + p.L - 1) / p.L, a.nch * nimg);
+    fwd_pass_a_kernel<<<ga, 256, f.smem, s>>>(a.img, a.tmp, a.deapod, f.tw, p, a.nch, a.nc_total, a.ch0, a.half_in);
     TRON_CUDA(cudaGetLastError());
-    dim3 gb((f.n + p.L - 1) / p.L, a.nch);
+    dim3 gb((f.n + p.L - 1) / p.L, a.nch * nimg);
     fwd_pass_b_kernel<<<gb, 256, f.smem, s>>>(a.tmp, a.grid, f.tw, p);
     TRON_CUDA(cudaGetLastError());
     return 0;

@@ -494,8 +494,8 @@ __device__ __forceinline__ void grid_heavy_path(const GridLaunch &g, int hg, int
  * Grid: x = slice group, y = heavy block / tile rank, z = channel chunk (launch_grid_cg).
  * BT threads per block: 256 (16x16 tile), or 128 (16x8 tile) where the accumulators need the
  * registers: 5 blocks of 128 threads leave 96 registers per thread, 3 of 256 only 80. */
-template <int CH, int GS, bool HALF, int BT, bool PLAIN>
-__global__ void __launch_bounds__(BT, (BT == 128 ? 5 : 4))
+template <int CH, int GS, bool HALF, int BT, bool PLAIN, int MB>
+__global__ void __launch_bounds__(BT, MB)
 grid_gather_kernel(const GridLaunch g, const int rank0)
 {
     constexpr int WARPS = BT / 32;
@@ -520,7 +520,12 @@ static int launch_grid_cghp(const GridLaunch &g, cudaStream_t s)
     const int ranks = tiles + (g.nheavy + BT / 32 - 1) / (BT / 32);
     for (int r0 = 0; r0 < ranks; r0 += 65535) {            /* gridDim.y limit */
         dim3 grid(g.ngroups, std::min(65535, ranks - r0), g.nch / CH);
-        grid_gather_kernel<CH, GS, HALF, BT, PLAIN><<<grid, BT, 0, s>>>(g, r0);
+        static const int mb_try = getenv("TRON_GRID_MB") ? atoi(getenv("TRON_GRID_MB")) : 0;      /* experiment switch */
+        bool done = false;
+        if constexpr (BT == 128 && CH == 6 && GS == 4 && !HALF && PLAIN) {
+            if (mb_try == 6) { grid_gather_kernel<CH, GS, HALF, BT, PLAIN, 6><<<grid, BT, 0, s>>>(g, r0); done = true; }
+        }
+        if (!done) grid_gather_kernel<CH, GS, HALF, BT, PLAIN, (BT == 128 ? 5 : 4)><<<grid, BT, 0, s>>>(g, r0);
         TRON_CUDA(cudaGetLastError());
     }
     return 0;

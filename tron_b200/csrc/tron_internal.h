@@ -57,6 +57,8 @@ struct DegridLaunch {
     int n, nro, npe, nc_total, ch0, nch;
     KbParams kb;
     int half_out;
+    int nimg = 1;                 /* grids per launch: samples [nimg][npe][nro][nc_total], grid [nimg][nch][n][n] */
+    int cs_stride = 0;            /* entries between the spoke tables of consecutive grids (0: shared) */
 };
 
 int launch_grid(const GridLaunch &g, cudaStream_t s);
@@ -104,6 +106,7 @@ struct FwdFftLaunch {
     const float *deapod;          /* [nkeep][nkeep] reciprocal weights of the padded region */
     int nch, nc_total, ch0;
     int half_in;
+    int nimg = 1;                 /* images per launch: img [nimg][nx][nx][nc_total], tmp/grid [nimg][nch]... */
 };
 int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s);
 int launch_deapod_tables(float *adj_tab, float *fwd_tab, int nx, int nxos, float W, float gridos, cudaStream_t s);
