@@ -168,6 +168,7 @@ template <int CPL, bool HALF>
 __global__ void __launch_bounds__(256)
 walsh_wide_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int nimg, int nc, int npatch)
 {
+    constexpr int WCH = CPL >= 4 ? 2 : 4;
     const int lane = threadIdx.x & 31;
     const size_t npix = (size_t)nimg * nimg;
     const float2 *src = coil + (size_t)blockIdx.y * npix * nc;
@@ -183,23 +184,37 @@ walsh_wide_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int n
         for (int it = 0; it < 5; ++it) {
 #pragma unroll
             for (int i = 0; i < CPL; ++i) yv[i] = make_float2(0.f, 0.f);
+            /* a patch row in chunks of WCH pixels: WCH independent dot products are reduced together,
+             * so the shuffle latencies overlap instead of forming one dependent chain per pixel */
             for (int px = x0; px <= x1; ++px)
-                for (int py = y0; py <= y1; ++py) {
-                    const float2 *p = src + ((size_t)px * nimg + py) * nc;
-                    float2 z[CPL];
-                    float2 d = make_float2(0.f, 0.f);   /* z_q^H x */
+                for (int pyc = y0; pyc <= y1; pyc += WCH) {
+                    const float2 *p = src + ((size_t)px * nimg + pyc) * nc;
+                    float2 z[WCH][CPL], d[WCH];
 #pragma unroll
-                    for (int i = 0; i < CPL; ++i) {
-                        z[i] = lane + 32 * i < nc ? __ldg(p + lane + 32 * i) : make_float2(0.f, 0.f);
-                        float2 m = cmulc_(xv[i], z[i]);
-                        d.x += m.x; d.y += m.y;
-                    }
-                    d.x = warp_sum(d.x); d.y = warp_sum(d.y);
+                    for (int j = 0; j < WCH; ++j) {
+                        const bool okj = pyc + j <= y1;
+                        d[j] = make_float2(0.f, 0.f);    /* z_q^H x */
 #pragma unroll
-                    for (int i = 0; i < CPL; ++i) {
-                        float2 m = cmul_(z[i], d);
-                        yv[i].x += m.x; yv[i].y += m.y;
+                        for (int i = 0; i < CPL; ++i) {
+                            z[j][i] = (okj && lane + 32 * i < nc) ? __ldg(p + (size_t)j * nc + lane + 32 * i) : make_float2(0.f, 0.f);
+                            float2 m = cmulc_(xv[i], z[j][i]);
+                            d[j].x += m.x; d[j].y += m.y;
+                        }
                     }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int j = 0; j < WCH; ++j) {
+                            d[j].x += __shfl_xor_sync(0xffffffffu, d[j].x, o);
+                            d[j].y += __shfl_xor_sync(0xffffffffu, d[j].y, o);
+                        }
+#pragma unroll
+                    for (int j = 0; j < WCH; ++j)
+#pragma unroll
+                        for (int i = 0; i < CPL; ++i) {
+                            float2 m = cmul_(z[j][i], d[j]);
+                            yv[i].x += m.x; yv[i].y += m.y;
+                        }
                 }
             float nsq = 0.f;
 #pragma unroll

@@ -520,12 +520,10 @@ static int launch_grid_cghp(const GridLaunch &g, cudaStream_t s)
     const int ranks = tiles + (g.nheavy + BT / 32 - 1) / (BT / 32);
     for (int r0 = 0; r0 < ranks; r0 += 65535) {            /* gridDim.y limit */
         dim3 grid(g.ngroups, std::min(65535, ranks - r0), g.nch / CH);
-        static const int mb_try = getenv("TRON_GRID_MB") ? atoi(getenv("TRON_GRID_MB")) : 0;      /* experiment switch */
-        bool done = false;
-        if constexpr (BT == 128 && CH == 6 && GS == 4 && !HALF && PLAIN) {
-            if (mb_try == 6) { grid_gather_kernel<CH, GS, HALF, BT, PLAIN, 6><<<grid, BT, 0, s>>>(g, r0); done = true; }
-        }
-        if (!done) grid_gather_kernel<CH, GS, HALF, BT, PLAIN, (BT == 128 ? 5 : 4)><<<grid, BT, 0, s>>>(g, r0);
+        /* 128-thread blocks: 6 per SM (80 registers, 57 words of spill on the cold paths) measured 2 % faster
+         * than 5 per SM (96 registers, no spill) for the 6-channel 4-slice instantiation; the others keep 5 */
+        constexpr int MB = BT == 128 ? ((CH == 6 && GS == 4 && !HALF && PLAIN) ? 6 : 5) : 4;
+        grid_gather_kernel<CH, GS, HALF, BT, PLAIN, MB><<<grid, BT, 0, s>>>(g, r0);
         TRON_CUDA(cudaGetLastError());
     }
     return 0;
