@@ -167,13 +167,13 @@ static int cg_apply_adjoint(tron_plan *p, const void *samples, int half, int dat
 {
     const tron_geometry &g = p->g;
     GridLaunch L = make_grid_launch(p, samples, p->d_grid, z0, nb);
-    L.slide = data_slide; L.half_in = half;
+    L.slide = data_slide; L.half_in = half; L.zero_r2 = p->zero_r2;
     int rc = launch_grid(L, s);
     if (rc) return rc;
     AdjFftLaunch a;
     a.grid = p->d_grid; a.tmp = p->d_tmp; a.deapod = deapod; a.out = coil;
     a.nslices = nb; a.nch = p->nch; a.nc_total = g.nc * g.nt; a.ch0 = g.coil_begin;
-    a.mode = 2; a.half_out = 0;
+    a.mode = 2; a.half_out = 0; a.zero_r2 = p->zero_r2;
     p->last_launches += 3;
     return launch_adj_fft(p->fft, a, s);
 }

@@ -453,7 +453,8 @@ __device__ __forceinline__ float2 *p2_fft(float2 (&v)[8], float2 *lineA, float2 
 
 template <int N, int L>
 __global__ void __launch_bounds__(L *(N / 8))
-p2_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep)
+p2_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep,
+              int zero_r2)
 {
     extern __shared__ float2 smem[];
     constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
@@ -464,8 +465,12 @@ p2_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const f
     for (int i = threadIdx.x; i < N; i += L * T) stw[phys(i)] = tw[i];
     const float2 *g = grid + plane * (size_t)N * N + (size_t)(y0 + l) * N;
     float2 v[8];
+    const int Yc = y0 + l - N / 2, lim = zero_r2 - Yc * Yc;       /* see p2w_adj_pass_a */
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = g[j + q * T];
+    for (int q = 0; q < 8; ++q) {
+        const int X = j + q * T - N / 2;
+        v[q] = X * X <= lim ? g[j + q * T] : make_float2(0.f, 0.f);
+    }
     __syncthreads();
     float2 *res = p2_fft<N, +1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j, l) - l * PITCH;
     const int w = (N - nkeep) / 2, h = N / 2;
@@ -729,7 +734,8 @@ __device__ __forceinline__ void p2w_stage2(float2 (&a)[N / R1], int b, const flo
  * transposed, coalesced store. */
 template <int N, int R1>
 __global__ void __launch_bounds__(P2W<N, R1>::THREADS, 5)
-p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep)
+p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep,
+               int zero_r2)
 {
     extern __shared__ float2 smem[];
     using G = P2W<N, R1>;
@@ -741,9 +747,16 @@ p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const 
     const size_t plane = blockIdx.y;
     const float2 *g = grid + plane * (size_t)N * N + (size_t)(y0 + l) * N + j;
     {
+        /* cells with X^2 + Y^2 > zero_r2 hold no sample (annulus of tron.cu:498-502 beyond nxos/2-1+W):
+         * the gridding kernel does not store them and they are not fetched -- a fifth of the grid */
+        const int Y = y0 + l - N / 2, X0 = j - N / 2;
+        const int lim = zero_r2 - Y * Y;
         float2 v[R1];
 #pragma unroll
-        for (int q = 0; q < R1; ++q) v[q] = g[q * G::T];
+        for (int q = 0; q < R1; ++q) {
+            const int X = X0 + q * G::T;
+            v[q] = X * X <= lim ? g[q * G::T] : make_float2(0.f, 0.f);
+        }
         p2w_stage1<N, R1, +1>(v, xline, j);
     }
     __syncwarp();
@@ -864,7 +877,7 @@ template <int N, int R1> struct P2WLaunch {
     static int adj_a(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
     {
         dim3 ga(N / G::L, a.nslices * a.nch);
-        p2w_adj_pass_a<N, R1><<<ga, G::THREADS, smem_a(f.nkeep), s>>>(a.grid, a.tmp, f.tw, f.nkeep);
+        p2w_adj_pass_a<N, R1><<<ga, G::THREADS, smem_a(f.nkeep), s>>>(a.grid, a.tmp, f.tw, f.nkeep, a.zero_r2);
         TRON_CUDA(cudaGetLastError());
         return 0;
     }
@@ -894,7 +907,7 @@ template <int N, int L> struct P2Launch {
             if constexpr (P2WSplit<N>::R1 != 0) { int rc = P2WLaunch<N, P2WSplit<N>::R1>::adj_a(f, a, s); if (rc) return rc; }
         } else {
             dim3 ga(N / L, a.nslices * a.nch);
-            p2_adj_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.grid, a.tmp, f.tw, f.nkeep);
+            p2_adj_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.grid, a.tmp, f.tw, f.nkeep, a.zero_r2);
             TRON_CUDA(cudaGetLastError());
         }
         if constexpr (P2WSplit<N>::R1 != 0) {

@@ -441,6 +441,10 @@ __device__ __forceinline__ void grid_tile_path(const GridLaunch &g, int rank, in
     const int x = (tile & 0xffff) * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = (tile >> 16) * (BT / 16) + (warp >> 1) * 4 + (lane >> 3);
     if (x >= n || y >= n) return;
+    {
+        const int X = x - n / 2, Y = y - n / 2;
+        if (X * X + Y * Y > g.zero_r2) return;            /* beyond the last annulus: never fetched by the FFT pass */
+    }
 
     const float4 *tab; const int *lut; const char *samples;
     group_pointers<CH, GS, HALF>(g, grp, chunk, tab, lut, samples);

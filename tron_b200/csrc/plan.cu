@@ -238,6 +238,14 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
                                      g.npe1work, 0, 1, 1, n, cfg->kernwidth, p->stream));
     }
     PLAN_TRY(fft_plan_init(p->fft, n, g.nx));
+    if (cfg->adjoint && p->fft.pow2 && !getenv("TRON_NO_ZERO_SKIP")) {
+        /* a cell receives samples only if ceil(R - W) <= nxos/2 - 1 (tron.cu:498-502): beyond
+         * R = nxos/2 - 1 + W (+0.5 of margin for the float hypot) the grid is identically zero; the
+         * gridding kernel skips those stores and FFT pass A does not fetch them (same integer test) */
+        const float rz = (float)(n / 2 - 1) + cfg->kernwidth + 0.5f;
+        const double r2 = (double)rz * (double)rz;
+        p->zero_r2 = r2 < 2.0e9 ? (int)r2 : 0x7fffffff;
+    }
     if (cfg->adjoint) {
         PLAN_TRY(build_tile_order(&p->tile_order, n, 16));
         PLAN_TRY(build_tile_order(&p->tile_order8, n, 8));
@@ -317,6 +325,7 @@ GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d
     L.sdc_as = L.sdc_a * L.scale; L.sdc_bs = L.sdc_b * L.scale;
     L.half_in = p->cfg.half_in;
     L.dbg = p->grid_dbg;
+    L.zero_r2 = 0x7fffffff;                              /* stage API: every cell is stored */
     return L;
 }
 } // namespace tronb
@@ -332,6 +341,7 @@ static int adjoint_mode(const tron_plan *p)
 static int launch_batch_grid(tron_plan *p, const void *d_in, float2 *d_grid, int z0, int nb, cudaStream_t s)
 {
     GridLaunch L = make_grid_launch(p, d_in, d_grid, z0, nb);
+    L.zero_r2 = p->zero_r2;
     p->last_launches += 1;
     return launch_grid(L, s);
 }
@@ -343,6 +353,7 @@ static int launch_batch_fft(tron_plan *p, void *d_out, const float2 *d_grid, int
     a.grid = d_grid; a.tmp = p->d_tmp; a.deapod = p->deapod_adj;
     a.nslices = nb; a.nch = p->nch; a.nc_total = g.nc * g.nt; a.ch0 = g.coil_begin;
     a.mode = adjoint_mode(p); a.half_out = p->cfg.half_out;
+    a.zero_r2 = p->zero_r2;
     size_t per = (size_t)g.nx * g.ny * (a.mode == 2 ? (size_t)g.nc : 1);
     a.out = (char *)d_out + (size_t)z0 * per * p->out_elem_bytes;
     p->last_launches += 2;

@@ -48,6 +48,8 @@ struct GridLaunch {               /* everything the gridding kernel needs */
     float sdc_as, sdc_bs;         /* sdc_a * scale, sdc_b * scale: the gather folds the output scale into the weight */
     int half_in;
     long long *dbg;               /* optional per-warp cycle counts [blocks][8] */
+    int zero_r2;                  /* cells with X^2 + Y^2 > zero_r2 can hold no sample and are NOT stored (the FFT pass
+                                     that follows does not fetch them); INT_MAX: every cell is stored */
 };
 
 struct DegridLaunch {
@@ -96,6 +98,7 @@ struct AdjFftLaunch {
     int mode;                     /* 0 rss (complex64 out), 1 single-channel complex, 2 per-coil interleaved,
                                      3 partial sum of squares (float) */
     int half_out;
+    int zero_r2 = 0x7fffffff;     /* grid cells with X^2 + Y^2 > zero_r2 are known to be zero and are not read */
 };
 int launch_adj_fft(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s);
 
@@ -147,6 +150,7 @@ struct tron_plan {
     int *tile_order = nullptr, *tile_order8 = nullptr, *heavy_cells = nullptr;
     long long *grid_dbg = nullptr;       /* TRON_GRID_DEBUG: per-warp cycles of the last gridding launch */
     int nheavy = 0, heavy_r2 = -1;
+    int zero_r2 = 0x7fffffff;            /* adjoint: cells beyond this squared radius never receive a sample */
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
     float2 *d_gridi = nullptr;                      /* forward, nc >= 32: channel-interleaved copy of the grid */
     float2 *d_coil = nullptr;                       /* per-coil images of a batch (Walsh combine, CGNR iterate x) */
