@@ -168,7 +168,8 @@ template <int CPL, bool HALF>
 __global__ void __launch_bounds__(256)
 walsh_wide_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int nimg, int nc, int npatch)
 {
-    constexpr int WCH = CPL >= 4 ? 2 : 4;
+    constexpr int WCH = 1;   /* measured: the kernel is bound by SHFL throughput (10 per patch pixel), not by their latency;
+                                reducing 4 pixels per round was no faster (nc = 32) or slower (nc = 64) */
     const int lane = threadIdx.x & 31;
     const size_t npix = (size_t)nimg * nimg;
     const float2 *src = coil + (size_t)blockIdx.y * npix * nc;
@@ -184,8 +185,7 @@ walsh_wide_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int n
         for (int it = 0; it < 5; ++it) {
 #pragma unroll
             for (int i = 0; i < CPL; ++i) yv[i] = make_float2(0.f, 0.f);
-            /* a patch row in chunks of WCH pixels: WCH independent dot products are reduced together,
-             * so the shuffle latencies overlap instead of forming one dependent chain per pixel */
+            /* a patch row in chunks of WCH pixels whose dot products are reduced together */
             for (int px = x0; px <= x1; ++px)
                 for (int pyc = y0; pyc <= y1; pyc += WCH) {
                     const float2 *p = src + ((size_t)px * nimg + pyc) * nc;
