@@ -246,3 +246,25 @@ def test_legacy_cgnr_symbol(lib, oracle):
     torch.cuda.synchronize()
     assert torch.allclose(z, y + 0.25 * x, atol=1e-6)
     lib.tron_shutdown()
+
+
+@pytest.mark.parametrize("nro", [512, 256])
+def test_percoil_output_two_stage_fft_matches_radix8_and_rss(lib, monkeypatch, nro):
+    """Per-coil images at the benchmark line lengths come from the two-stage pass B
+    (p2w_adj_pass_b_coil); they must agree with the radix-8 pass and reproduce the RSS image."""
+    import tron_b200 as t
+    torch_cuda()
+    dims = [6, 1, nro, 90, 1]
+    flags = dict(adjoint=True, golden=True, undersamp=0.1, prof_slide=13)
+    h_in = synth_complex((int(np.prod(dims)),), stream=66)
+    nx = nro // 2
+    with t.Plan(t.make_config(dims, per_coil_out=True, **flags)) as p:
+        coils = p.recon_host(h_in).reshape(p.geom.nz, nx, nx, 6)
+    with t.Plan(t.make_config(dims, **flags)) as p:
+        rss = p.recon_host(h_in).reshape(p.geom.nz, nx, nx)
+    monkeypatch.setenv("TRON_FFT_R8", "1")
+    with t.Plan(t.make_config(dims, per_coil_out=True, **flags)) as p:
+        coils8 = p.recon_host(h_in).reshape(coils.shape)
+    assert rel_l2(coils, coils8) <= 2e-6
+    assert rel_l2(np.sqrt((np.abs(coils.astype(np.complex128)) ** 2).sum(-1)), rss.real) <= 2e-6
+    assert np.all(rss.imag == 0)

@@ -857,6 +857,64 @@ p2w_adj_pass_b_sos(const float2 *__restrict__ tmp, void *__restrict__ outv, cons
     }
 }
 
+/* adjoint pass B, nkeep = N/2, coils kept apart: mode 1 (single channel, complex image) and mode 2
+ * (per-coil images, channel interleaved -- the input of the Walsh combine and the vectors of CGNR).
+ * Same line transform as p2w_adj_pass_b_sos; each coil's kept outputs are staged as F[line][a] in a
+ * buffer of their own (the exchange buffer stays live for the next coil) and stored transposed. */
+template <int N, int R1>
+__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 4)
+p2w_adj_pass_b_coil(const float2 *__restrict__ tmp, void *__restrict__ outv, const float *__restrict__ deapod,
+                    const float2 *__restrict__ tw, int nch, int nc_total, int ch0, int mode, int half_out)
+{
+    extern __shared__ float2 smem[];
+    using G = P2W<N, R1>;
+    constexpr int nkeep = N / 2, KT = G::R2 / 4;
+    constexpr int PF = G::fpitch(nkeep);
+    const int l = threadIdx.x / G::T, j = threadIdx.x % G::T;
+    float2 *xline = smem + l * G::LPX;
+    float2 *F = smem + G::L * G::LPX;
+    const int b0 = blockIdx.x * G::L;
+    const int slice = blockIdx.y;
+    const size_t img = (size_t)nkeep * nkeep;
+    const float2 *src = tmp + ((size_t)slice * nch * nkeep + b0 + l) * (size_t)N + j;
+    for (int ch = 0; ch < nch; ++ch) {
+        {
+            float2 v[R1];
+#pragma unroll
+            for (int q = 0; q < R1; ++q) v[q] = src[q * G::T];
+            p2w_stage1<N, R1, +1>(v, xline, j);
+        }
+        src += (size_t)nkeep * N;
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < G::M2; ++m) {
+            const int b = j + m * G::T;
+            float2 a[G::R2];
+            p2w_stage2_load<N, R1>(a, xline, b);
+            p2w_stage2<N, R1, +1>(a, b, tw);
+            const float sg = (b & 1) ? -1.f : 1.f;    /* input shift by N/2 = (-1)^k on the output */
+#pragma unroll
+            for (int u = 0; u < 2 * KT; ++u) {
+                const int t = u < KT ? u : G::R2 - 2 * KT + u;
+                const int aa = (b + t * R1 + N / 4) & (N - 1);
+                F[l * PF + aa] = make_float2(a[t].x * sg, a[t].y * sg);
+            }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nkeep * G::L; idx += G::THREADS) {
+            const int aa = idx / G::L, ll = idx % G::L;
+            const size_t pix = (size_t)aa * nkeep + b0 + ll;
+            const float d = __ldg(deapod + pix);
+            float2 val = F[ll * PF + aa];
+            val.x *= d; val.y *= d;
+            const size_t o = mode == 1 ? (size_t)slice * img + pix : ((size_t)slice * img + pix) * nc_total + ch0 + ch;
+            if (half_out) ((__half2 *)outv)[o] = __float22half2_rn(val);
+            else ((float2 *)outv)[o] = val;
+        }
+        __syncthreads();                              /* F and the exchange buffers are free again */
+    }
+}
+
 template <int N, int R1> struct P2WLaunch {
     using G = P2W<N, R1>;
     static size_t smem_a(int nkeep) { return (size_t)std::max(G::L * G::LPX, G::L * G::fpitch(nkeep)) * sizeof(float2); }
@@ -864,6 +922,17 @@ template <int N, int R1> struct P2WLaunch {
     {
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_a<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_b_sos<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N / 2)));
+        TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_b_coil<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coil()));
+        return 0;
+    }
+    static size_t smem_coil() { return (size_t)(G::L * G::LPX + G::L * G::fpitch(N / 2)) * sizeof(float2); }
+    /* per-coil pass B; only for nkeep = N/2 and modes 1 / 2 */
+    static int adj_b_coil(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
+    {
+        dim3 gb(f.nkeep / G::L, a.nslices);
+        p2w_adj_pass_b_coil<N, R1><<<gb, G::THREADS, smem_coil(), s>>>(a.tmp, a.out, a.deapod, f.tw, a.nch, a.nc_total,
+                                                                       a.ch0, a.mode, a.half_out);
+        TRON_CUDA(cudaGetLastError());
         return 0;
     }
     /* sum-of-squares pass B; only for nkeep = N/2 and modes 0 / 3 */
@@ -912,6 +981,7 @@ template <int N, int L> struct P2Launch {
         }
         if constexpr (P2WSplit<N>::R1 != 0) {
             if (wide_a && 2 * f.nkeep == N && (a.mode == 0 || a.mode == 3)) return P2WLaunch<N, P2WSplit<N>::R1>::adj_b_sos(f, a, s);
+            if (wide_a && 2 * f.nkeep == N) return P2WLaunch<N, P2WSplit<N>::R1>::adj_b_coil(f, a, s);
         }
         dim3 gb((f.nkeep + L - 1) / L, a.nslices);
         if (2 * f.nkeep <= N)
