@@ -46,13 +46,13 @@ __device__ __forceinline__ double block_sum(double v)
 
 /* z [nb][nx][nx][nc]: clear row 0 and column 0, part[b][blockIdx.x] = partial |z_b|^2 */
 __global__ void __launch_bounds__(CG_THREADS)
-cg_zz_kernel(float2 *__restrict__ z, double *__restrict__ part, int nx, int nc, int planar)
+cg_zz_kernel(float2 *__restrict__ z, double *__restrict__ part, int nx, int nc)
 {
-    const size_t N = (size_t)nx * nx * nc, npix = (size_t)nx * nx;
+    const size_t N = (size_t)nx * nx * nc;
     float2 *zb = z + (size_t)blockIdx.y * N;
     float acc = 0.f;
     for (size_t i = (size_t)blockIdx.x * CG_THREADS + threadIdx.x; i < N; i += (size_t)gridDim.x * CG_THREADS) {
-        const size_t pix = planar ? i % npix : i / nc;
+        const size_t pix = i / nc;
         if (pix < (size_t)nx || pix % nx == 0) { zb[i] = make_float2(0.f, 0.f); continue; }
         const float2 q = zb[i];
         acc += q.x * q.x + q.y * q.y;
@@ -173,7 +173,7 @@ static int cg_apply_adjoint(tron_plan *p, const void *samples, int half, int dat
     AdjFftLaunch a;
     a.grid = p->d_grid; a.tmp = p->d_tmp; a.deapod = deapod; a.out = coil;
     a.nslices = nb; a.nch = p->nch; a.nc_total = g.nc * g.nt; a.ch0 = g.coil_begin;
-    a.mode = p->percoil_planar ? 4 : 2; a.half_out = 0; a.zero_r2 = p->zero_r2;
+    a.mode = 2; a.half_out = 0; a.zero_r2 = p->zero_r2;
     p->last_launches += 3;
     return launch_adj_fft(p->fft, a, s);
 }
@@ -197,7 +197,7 @@ int run_percoil_batch(tron_plan *p, const void *d_in, int z0, int nb, cudaStream
 
     int rc = cg_apply_adjoint(p, d_in, p->cfg.half_in, g.prof_slide, p->cg_z, z0, nb, p->deapod_fwd, s);
     if (rc) return rc;
-    cg_zz_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_z, part_zz[0], g.nx, nc, p->percoil_planar);
+    cg_zz_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_z, part_zz[0], g.nx, nc);
     cg_dir_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_p, p->cg_z, part_zz[0], part_zz[0], N, 1);
     TRON_CUDA(cudaMemsetAsync(x, 0, (size_t)nb * N * sizeof(float2), s));
     if (niter > 1) {
@@ -212,7 +212,6 @@ int run_percoil_batch(tron_plan *p, const void *d_in, int z0, int nb, cudaStream
             FwdFftLaunch f;
             f.img = p->cg_p; f.tmp = p->d_tmp; f.grid = p->d_grid; f.deapod = p->deapod_fwd;
             f.nch = p->nch; f.nc_total = nc; f.ch0 = g.coil_begin; f.half_in = 0; f.nimg = nb;
-            f.planar_in = p->percoil_planar;
             rc = launch_fwd_fft(p->fft, f, s);
             if (rc) return rc;
             DegridLaunch d;
@@ -238,7 +237,7 @@ int run_percoil_batch(tron_plan *p, const void *d_in, int z0, int nb, cudaStream
         const char *r0 = (const char *)p->cg_r - (ptrdiff_t)z0 * (ptrdiff_t)(n * sizeof(float2));
         rc = cg_apply_adjoint(p, r0, 0, g.npe1work, p->cg_z, z0, nb, p->deapod_fwd, s);
         if (rc) return rc;
-        cg_zz_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_z, part_zz[(t + 1) & 1], g.nx, nc, p->percoil_planar);
+        cg_zz_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_z, part_zz[(t + 1) & 1], g.nx, nc);
         cg_dir_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_p, p->cg_z, part_zz[(t + 1) & 1], part_zz[t & 1], N, 0);
         TRON_CUDA(cudaGetLastError());
         p->last_launches += 2;

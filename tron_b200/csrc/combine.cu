@@ -43,41 +43,35 @@ __device__ __forceinline__ void store_px(void *out, size_t i, float2 v)
 /* ---------------------------------------------------------------------- */
 /* mode 0: (sqrt(sum_c |z_c|^2), 0), sequential over c (tron.cu:259-264); 1: single channel passes
  * through as complex (tron.cu:265-266); 2: copy of the per-coil images; 3: the sum itself, float32 */
-__global__ void coil_combine_kernel(void *__restrict__ out, const float2 *__restrict__ coil, size_t npix, int nslices,
-                                    int nc, int mode, int half_out, int planar)
+__global__ void coil_combine_kernel(void *__restrict__ out, const float2 *__restrict__ coil, size_t npix, int nc,
+                                    int mode, int half_out)
 {
-    const size_t total = npix * nslices;
-    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
-        /* channel c of pixel id: interleaved coil[id*nc + c], planar coil[(slice*nc + c)*npix + pix] */
-        const size_t slice = id / npix, pix = id - slice * npix;
-        const size_t base = planar ? slice * nc * npix + pix : id * nc;
-        const size_t cs = planar ? npix : 1;
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < npix; id += (size_t)gridDim.x * blockDim.x) {
         if (mode == 2) {
             for (int c = 0; c < nc; ++c) {
-                float2 z = coil[base + c * cs];
+                float2 z = coil[id * nc + c];
                 if (half_out) store_px<true>(out, id * nc + c, z); else store_px<false>(out, id * nc + c, z);
             }
             continue;
         }
         if (mode == 1) {
-            float2 z = coil[base];
+            float2 z = coil[id];
             if (half_out) store_px<true>(out, id, z); else store_px<false>(out, id, z);
             continue;
         }
         float val = 0.f;
-        for (int c = 0; c < nc; ++c) { float2 z = coil[base + c * cs]; val += z.x * z.x + z.y * z.y; }
+        for (int c = 0; c < nc; ++c) { float2 z = coil[id * nc + c]; val += z.x * z.x + z.y * z.y; }
         if (mode == 3) ((float *)out)[id] = val;
         else if (half_out) store_px<true>(out, id, make_float2(sqrtf(val), 0.f));
         else store_px<false>(out, id, make_float2(sqrtf(val), 0.f));
     }
 }
 
-int launch_coil_combine(void *out, const float2 *coil, size_t npix, int nslices, int nc, int mode, int half_out,
-                        int planar, cudaStream_t s)
+int launch_coil_combine(void *out, const float2 *coil, size_t npix, int nc, int mode, int half_out, cudaStream_t s)
 {
-    size_t blocks = (npix * nslices + 255) / 256;
+    size_t blocks = (npix + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    coil_combine_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, coil, npix, nslices, nc, mode, half_out, planar);
+    coil_combine_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, coil, npix, nc, mode, half_out);
     TRON_CUDA(cudaGetLastError());
     return 0;
 }
@@ -85,24 +79,17 @@ int launch_coil_combine(void *out, const float2 *coil, size_t npix, int nslices,
 /* ---------------------------------------------------------------------- */
 /* Walsh, nc <= 8: registers                                               */
 /* ---------------------------------------------------------------------- */
-/* the NC channels of pixel `pix`: interleaved (16-byte loads) or planar (one coalesced 8-byte load per plane) */
-template <int NC, bool PL>
-__device__ __forceinline__ void load_px(float2 (&z)[NC], const float2 *src, size_t pix, size_t npix)
+template <int NC>
+__device__ __forceinline__ void load_px(float2 (&z)[NC], const float2 *p)
 {
-    if (PL) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) z[i] = __ldg(src + (size_t)i * npix + pix);
-    } else {
-        const float2 *p = src + pix * NC;
-#pragma unroll
-        for (int i = 0; i < NC / 2; ++i) {
-            float4 q = __ldg((const float4 *)p + i);
-            z[2 * i] = make_float2(q.x, q.y); z[2 * i + 1] = make_float2(q.z, q.w);
-        }
+    for (int i = 0; i < NC / 2; ++i) {
+        float4 q = __ldg((const float4 *)p + i);
+        z[2 * i] = make_float2(q.x, q.y); z[2 * i + 1] = make_float2(q.z, q.w);
     }
 }
 
-template <int NC, bool HALF, bool PL>
+template <int NC, bool HALF>
 __global__ void __launch_bounds__(128)
 walsh_small_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int nimg, int npatch)
 {
@@ -119,7 +106,7 @@ walsh_small_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int 
         for (int px = x0; px <= x1; ++px)
             for (int py = y0; py <= y1; ++py) {
                 float2 z[NC];
-                load_px<NC, PL>(z, src, (size_t)px * nimg + py, npix);
+                load_px<NC>(z, src + ((size_t)px * nimg + py) * NC);
                 int t = 0;
 #pragma unroll
                 for (int j = 0; j < NC; ++j)
@@ -156,7 +143,7 @@ walsh_small_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int 
             for (int k = 0; k < NC; ++k) xv[k] = make_float2(yv[k].x * inv, yv[k].y * inv);
         }
         float2 z[NC];
-        load_px<NC, PL>(z, src, (size_t)id, npix);
+        load_px<NC>(z, src + (size_t)id * NC);
         float2 o = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {                  /* conj(x_c) z_c, tron.cu:294 */
@@ -250,52 +237,40 @@ walsh_wide_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int n
     }
 }
 
-template <bool HALF, bool PL>
-static int launch_walsh_small(void *out, const float2 *coil, int nimg, int nc, int npatch, int nslices, cudaStream_t s)
-{
-    const size_t npix = (size_t)nimg * nimg;
-    dim3 grid((unsigned)((npix + 127) / 128), nslices);
-    switch (nc) {
-    case 2: walsh_small_kernel<2, HALF, PL><<<grid, 128, 0, s>>>(out, coil, nimg, npatch); break;
-    case 4: walsh_small_kernel<4, HALF, PL><<<grid, 128, 0, s>>>(out, coil, nimg, npatch); break;
-    case 6: walsh_small_kernel<6, HALF, PL><<<grid, 128, 0, s>>>(out, coil, nimg, npatch); break;
-    default: walsh_small_kernel<8, HALF, PL><<<grid, 128, 0, s>>>(out, coil, nimg, npatch); break;
-    }
-    TRON_CUDA(cudaGetLastError());
-    return 0;
-}
-
 template <bool HALF>
-static int launch_walsh_h(void *out, const float2 *coil, int nimg, int nc, int npatch, int nslices, int planar, cudaStream_t s)
+static int launch_walsh_h(void *out, const float2 *coil, int nimg, int nc, int npatch, int nslices, cudaStream_t s)
 {
     const size_t npix = (size_t)nimg * nimg;
     const bool aligned = ((uintptr_t)coil % 16) == 0;
-    if (nc <= 8 && nc % 2 == 0 && (planar || aligned)) {
-        return planar ? launch_walsh_small<HALF, true>(out, coil, nimg, nc, npatch, nslices, s)
-                      : launch_walsh_small<HALF, false>(out, coil, nimg, nc, npatch, nslices, s);
+    if (nc <= 8 && nc % 2 == 0 && aligned) {
+        dim3 grid((unsigned)((npix + 127) / 128), nslices);
+        switch (nc) {
+        case 2: walsh_small_kernel<2, HALF><<<grid, 128, 0, s>>>(out, coil, nimg, npatch); break;
+        case 4: walsh_small_kernel<4, HALF><<<grid, 128, 0, s>>>(out, coil, nimg, npatch); break;
+        case 6: walsh_small_kernel<6, HALF><<<grid, 128, 0, s>>>(out, coil, nimg, npatch); break;
+        default: walsh_small_kernel<8, HALF><<<grid, 128, 0, s>>>(out, coil, nimg, npatch); break;
+        }
+    } else {
+        size_t blocks = (npix + 7) / 8;                  /* 8 warps per block, one pixel per warp and trip */
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        dim3 grid((unsigned)blocks, nslices);
+        const int cpl = (nc + 31) / 32;
+        if (cpl == 1) walsh_wide_kernel<1, HALF><<<grid, 256, 0, s>>>(out, coil, nimg, nc, npatch);
+        else if (cpl == 2) walsh_wide_kernel<2, HALF><<<grid, 256, 0, s>>>(out, coil, nimg, nc, npatch);
+        else if (cpl <= 4) walsh_wide_kernel<4, HALF><<<grid, 256, 0, s>>>(out, coil, nimg, nc, npatch);
+        else { set_error("Walsh combine supports at most 128 channels (nc = %d)", nc); return TRON_EUNSUPPORTED; }
     }
-    if (planar) { set_error("planar coil images are only supported for nc <= 8"); return TRON_EINVAL; }
-    size_t blocks = (npix + 7) / 8;                      /* 8 warps per block, one pixel per warp and trip */
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    dim3 grid((unsigned)blocks, nslices);
-    const int cpl = (nc + 31) / 32;
-    if (cpl == 1) walsh_wide_kernel<1, HALF><<<grid, 256, 0, s>>>(out, coil, nimg, nc, npatch);
-    else if (cpl == 2) walsh_wide_kernel<2, HALF><<<grid, 256, 0, s>>>(out, coil, nimg, nc, npatch);
-    else if (cpl <= 4) walsh_wide_kernel<4, HALF><<<grid, 256, 0, s>>>(out, coil, nimg, nc, npatch);
-    else { set_error("Walsh combine supports at most 128 channels (nc = %d)", nc); return TRON_EUNSUPPORTED; }
     TRON_CUDA(cudaGetLastError());
     return 0;
 }
 
-/* coil [nslices][nimg][nimg][nc] (planar: [nslices][nc][nimg][nimg]) complex64 -> out [nslices][nimg][nimg]
- * complex64 (or complex-half) */
-int launch_walsh(void *out, const float2 *coil, int nimg, int nc, int npatch, int nslices, int half_out, int planar,
-                 cudaStream_t s)
+/* coil [nslices][nimg][nimg][nc] complex64 -> out [nslices][nimg][nimg] complex64 (or complex-half) */
+int launch_walsh(void *out, const float2 *coil, int nimg, int nc, int npatch, int nslices, int half_out, cudaStream_t s)
 {
     if (nslices <= 0) return 0;
-    if (nc == 1) return launch_coil_combine(out, coil, (size_t)nimg * nimg, nslices, 1, 1, half_out, 0, s);   /* tron.cu:277-278 */
-    return half_out ? launch_walsh_h<true>(out, coil, nimg, nc, npatch, nslices, planar, s)
-                    : launch_walsh_h<false>(out, coil, nimg, nc, npatch, nslices, planar, s);
+    if (nc == 1) return launch_coil_combine(out, coil, (size_t)nimg * nimg * nslices, 1, 1, half_out, s);   /* tron.cu:277-278 */
+    return half_out ? launch_walsh_h<true>(out, coil, nimg, nc, npatch, nslices, s)
+                    : launch_walsh_h<false>(out, coil, nimg, nc, npatch, nslices, s);
 }
 
 } // namespace tronb
@@ -306,12 +281,12 @@ extern "C" int tron_coilcombine_walsh_device(void *d_img, const void *d_coilimg,
                                              int nslices, void *stream)
 {
     if (!d_img || !d_coilimg || nimg < 1 || nchan < 1 || npatch < 0 || nslices < 1) { set_error("bad argument"); return TRON_EINVAL; }
-    return launch_walsh(d_img, (const float2 *)d_coilimg, nimg, nchan, npatch, nslices, 0, 0, (cudaStream_t)stream);
+    return launch_walsh(d_img, (const float2 *)d_coilimg, nimg, nchan, npatch, nslices, 0, (cudaStream_t)stream);
 }
 
 extern "C" int tron_coilcombine_sos_device(void *d_img, const void *d_coilimg, int nimg, int nchan, int nslices, void *stream)
 {
     if (!d_img || !d_coilimg || nimg < 1 || nchan < 1 || nslices < 1) { set_error("bad argument"); return TRON_EINVAL; }
-    return launch_coil_combine(d_img, (const float2 *)d_coilimg, (size_t)nimg * nimg, nslices, nchan,
-                               nchan > 1 ? 0 : 1, 0, 0, (cudaStream_t)stream);
+    return launch_coil_combine(d_img, (const float2 *)d_coilimg, (size_t)nimg * nimg * nslices, nchan,
+                               nchan > 1 ? 0 : 1, 0, (cudaStream_t)stream);
 }

@@ -146,7 +146,6 @@ int launch_degrid(const DegridLaunch &d, cudaStream_t s)
     size_t esz = d.half_out ? 4 : 8;
     bool aligned = (((uintptr_t)d.samples) % (2 * esz) == 0) && (d.nc_total % 2 == 0) && (d.ch0 % 2 == 0);
     if (!aligned || d.nch % 2) return launch_degrid_ch<1>(d, s);
-    if (d.nch % 6 == 0 && d.kb.W <= 3.0f) return launch_degrid_ch<6>(d, s);   /* weights once for six planes */
     if (d.nch % 4 == 0) return launch_degrid_ch<4>(d, s);
     return launch_degrid_ch<2>(d, s);
 }

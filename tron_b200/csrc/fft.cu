@@ -251,8 +251,7 @@ adj_pass_b_kernel(const float2 *__restrict__ tmp, void *__restrict__ outv, const
                         if (half_out) ((__half2 *)outv)[(size_t)slice * img + pix] = __float22half2_rn(v);
                         else ((float2 *)outv)[(size_t)slice * img + pix] = v;
                     } else {
-                        size_t o2 = mode == 4 ? ((size_t)slice * nch + ch) * img + pix
-                                              : ((size_t)slice * img + pix) * nc_total + ch0 + ch;
+                        size_t o2 = ((size_t)slice * img + pix) * nc_total + ch0 + ch;
                         if (half_out) ((__half2 *)outv)[o2] = __float22half2_rn(v);
                         else ((float2 *)outv)[o2] = v;
                     }
@@ -284,8 +283,7 @@ adj_pass_b_kernel(const float2 *__restrict__ tmp, void *__restrict__ outv, const
 /* ------- forward pass A: pad + deapodise on load, FFT along columns ------- */
 __global__ void __launch_bounds__(256)
 fwd_pass_a_kernel(const void *__restrict__ imgv, float2 *__restrict__ tmp, const float *__restrict__ deapod,
-                  const float2 *__restrict__ tw, const PassGeom p, int nch, int nc_total, int ch0, int half_in,
-                  int planar)
+                  const float2 *__restrict__ tw, const PassGeom p, int nch, int nc_total, int ch0, int half_in)
 {
     extern __shared__ float2 smem[];
     const int n = p.n, L = p.L, pitch = p.pitch, nx = p.nkeep;
@@ -301,8 +299,7 @@ fwd_pass_a_kernel(const void *__restrict__ imgv, float2 *__restrict__ tmp, const
         int l = idx / nx, b = idx - l * nx, a = a0 + l;
         /* pad drops source row 0 and column 0 (tron.cu:449-450) */
         if (a >= 1 && a < nx && b >= 1) {
-            size_t e = planar ? (size_t)blockIdx.y * nx * nx + (size_t)a * nx + b
-                              : img0 + ((size_t)a * nx + b) * nc_total + ch0 + ch;
+            size_t e = img0 + ((size_t)a * nx + b) * nc_total + ch0 + ch;
             float2 v = half_in ? __half22float2(((const __half2 *)imgv)[e]) : ((const float2 *)imgv)[e];
             float s = __ldg(deapod + (size_t)a * nx + b);
             bufA[l * pitch + phys(b + w)] = make_float2(v.x * s, v.y * s);
@@ -535,8 +532,7 @@ p2_adj_pass_b(const float2 *__restrict__ tmp, void *__restrict__ outv, const flo
                     if (half_out) ((__half2 *)outv)[(size_t)slice * img + pix] = __float22half2_rn(val);
                     else ((float2 *)outv)[(size_t)slice * img + pix] = val;
                 } else {
-                    const size_t o2 = mode == 4 ? ((size_t)slice * nch + ch) * img + pix
-                                                : ((size_t)slice * img + pix) * nc_total + ch0 + ch;
+                    const size_t o2 = ((size_t)slice * img + pix) * nc_total + ch0 + ch;
                     if (half_out) ((__half2 *)outv)[o2] = __float22half2_rn(val);
                     else ((float2 *)outv)[o2] = val;
                 }
@@ -566,7 +562,7 @@ p2_adj_pass_b(const float2 *__restrict__ tmp, void *__restrict__ outv, const flo
 template <int N, int L>
 __global__ void __launch_bounds__(L *(N / 8))
 p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const float *__restrict__ deapod,
-              const float2 *__restrict__ tw, int nx, int nch, int nc_total, int ch0, int half_in, int planar)
+              const float2 *__restrict__ tw, int nx, int nch, int nc_total, int ch0, int half_in)
 {
     extern __shared__ float2 smem[];
     constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
@@ -583,8 +579,7 @@ p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const flo
         const int b = j + q * T - w;                 /* source column of padded column j + q*T */
         v[q] = make_float2(0.f, 0.f);
         if (a >= 1 && a < nx && b >= 1 && b < nx) {  /* pad drops row 0 and column 0, tron.cu:449-450 */
-            const size_t e = planar ? (size_t)blockIdx.y * nx * nx + (size_t)a * nx + b
-                                    : img0 + ((size_t)a * nx + b) * nc_total + ch0 + ch;
+            const size_t e = img0 + ((size_t)a * nx + b) * nc_total + ch0 + ch;
             float2 x = half_in ? __half22float2(((const __half2 *)imgv)[e]) : ((const float2 *)imgv)[e];
             const float s = __ldg(deapod + (size_t)a * nx + b);
             v[q] = make_float2(x.x * s, x.y * s);
@@ -912,9 +907,7 @@ p2w_adj_pass_b_coil(const float2 *__restrict__ tmp, void *__restrict__ outv, con
             const float d = __ldg(deapod + pix);
             float2 val = F[ll * PF + aa];
             val.x *= d; val.y *= d;
-            const size_t o = mode == 1 ? (size_t)slice * img + pix
-                           : (mode == 4 ? ((size_t)slice * nch + ch) * img + pix
-                                        : ((size_t)slice * img + pix) * nc_total + ch0 + ch);
+            const size_t o = mode == 1 ? (size_t)slice * img + pix : ((size_t)slice * img + pix) * nc_total + ch0 + ch;
             if (half_out) ((__half2 *)outv)[o] = __float22half2_rn(val);
             else ((float2 *)outv)[o] = val;
         }
@@ -1004,8 +997,7 @@ template <int N, int L> struct P2Launch {
     {
         const int nimg = a.nimg > 0 ? a.nimg : 1;
         dim3 ga((f.nkeep + L - 1) / L, a.nch * nimg);
-        p2_fwd_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.img, a.tmp, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total, a.ch0, a.half_in,
-                                                      a.planar_in);
+        p2_fwd_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.img, a.tmp, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total, a.ch0, a.half_in);
         TRON_CUDA(cudaGetLastError());
         dim3 gb(N / L, a.nch * nimg);
         p2_fwd_pass_b<N, L><<<gb, THREADS, SMEM, s>>>(a.tmp, a.grid, f.tw, f.nkeep);
@@ -1151,8 +1143,7 @@ int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)
     PassGeom p = make_geom(f);
     const int nimg = a.nimg > 0 ? a.nimg : 1;
     dim3 ga((f.nkeep + p.L - 1) / p.L, a.nch * nimg);
-    fwd_pass_a_kernel<<<ga, 256, f.smem, s>>>(a.img, a.tmp, a.deapod, f.tw, p, a.nch, a.nc_total, a.ch0, a.half_in,
-                                              a.planar_in);
+    fwd_pass_a_kernel<<<ga, 256, f.smem, s>>>(a.img, a.tmp, a.deapod, f.tw, p, a.nch, a.nc_total, a.ch0, a.half_in);
     TRON_CUDA(cudaGetLastError());
     dim3 gb((f.n + p.L - 1) / p.L, a.nch * nimg);
     fwd_pass_b_kernel<<<gb, 256, f.smem, s>>>(a.tmp, a.grid, f.tw, p);

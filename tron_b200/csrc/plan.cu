@@ -192,9 +192,6 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     p->kb = make_kb(cfg->kernwidth);              /* plan-time polynomial fit, refmath.cuh */
     /* paths that need every coil image of a slice at once (combine.cu, cgnr.cu) */
     p->percoil = cfg->adjoint && (cfg->niter > 0 || (cfg->coil_combine == 1 && g.nc > 1));
-    /* planar per-coil images: coalesced stores from the FFT pass and coalesced loads in the combine and
-     * CGNR kernels; the warp-per-pixel Walsh kernel (nc > 8) wants the channels of a pixel contiguous */
-    p->percoil_planar = p->percoil && g.nc <= 8 && !getenv("TRON_PERCOIL_INTERLEAVED");
     p->in_elem_bytes = cfg->half_in ? 4 : 8;
     p->out_elem_bytes = cfg->half_out ? 4 : 8;
     if (cfg->adjoint && cfg->sos_partial && g.nc > 1) p->out_elem_bytes = 4;
@@ -375,8 +372,8 @@ static int launch_batch_percoil(tron_plan *p, void *d_out, const void *d_in, int
     void *out = (char *)d_out + (size_t)z0 * per * p->out_elem_bytes;
     p->last_launches += 1;
     if (p->cfg.coil_combine == 1 && g.nc > 1)
-        return launch_walsh(out, p->d_coil, g.nx, g.nc, p->cfg.walsh_npatch, nb, p->cfg.half_out, p->percoil_planar, s);
-    return launch_coil_combine(out, p->d_coil, (size_t)g.nx * g.ny, nb, g.nc, mode, p->cfg.half_out, p->percoil_planar, s);
+        return launch_walsh(out, p->d_coil, g.nx, g.nc, p->cfg.walsh_npatch, nb, p->cfg.half_out, s);
+    return launch_coil_combine(out, p->d_coil, (size_t)nb * g.nx * g.ny, g.nc, mode, p->cfg.half_out, s);
 }
 
 /* All adjoint slices of the plan.  Gridding (instruction-issue bound) runs on a low-priority

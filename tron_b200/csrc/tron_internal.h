@@ -96,7 +96,7 @@ struct AdjFftLaunch {
     const float *deapod;          /* [nkeep][nkeep] reciprocal weights */
     int nslices, nch, nc_total, ch0;
     int mode;                     /* 0 rss (complex64 out), 1 single-channel complex, 2 per-coil interleaved,
-                                     3 partial sum of squares (float), 4 per-coil planar [slice][ch][pix] (internal) */
+                                     3 partial sum of squares (float) */
     int half_out;
     int zero_r2 = 0x7fffffff;     /* grid cells with X^2 + Y^2 > zero_r2 are known to be zero and are not read */
 };
@@ -110,17 +110,13 @@ struct FwdFftLaunch {
     int nch, nc_total, ch0;
     int half_in;
     int nimg = 1;                 /* images per launch: img [nimg][nx][nx][nc_total], tmp/grid [nimg][nch]... */
-    int planar_in = 0;            /* img is [nimg][nch][nx][nx] (the internal per-coil layout) */
 };
 int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s);
 int launch_deapod_tables(float *adj_tab, float *fwd_tab, int nx, int nxos, float W, float gridos, cudaStream_t s);
 
 /* coil combination of channel-interleaved per-coil images (combine.cu) */
-/* planar = 0: coil [slice][pix][nc] (the reference's layout); 1: [slice][nc][pix] */
-int launch_coil_combine(void *out, const float2 *coil, size_t npix_per_slice, int nslices, int nc, int mode,
-                        int half_out, int planar, cudaStream_t s);
-int launch_walsh(void *out, const float2 *coil, int nimg, int nc, int npatch, int nslices, int half_out, int planar,
-                 cudaStream_t s);
+int launch_coil_combine(void *out, const float2 *coil, size_t npix, int nc, int mode, int half_out, cudaStream_t s);
+int launch_walsh(void *out, const float2 *coil, int nimg, int nc, int npatch, int nslices, int half_out, cudaStream_t s);
 
 } // namespace tronb
 
@@ -141,7 +137,6 @@ struct tron_plan {
     int nslices = 0;                     /* slices this plan owns */
     int batch = 1;
     int percoil = 0;                     /* adjoint through per-coil images: Walsh combine and/or CGNR */
-    int percoil_planar = 0;              /* those images are kept [slice][ch][pix] (nc <= 8) instead of interleaved */
     cudaStream_t stream = nullptr;       /* compute */
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaStream_t s_grid = nullptr, s_fft = nullptr;   /* low / high priority compute streams */
