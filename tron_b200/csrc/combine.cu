@@ -89,6 +89,19 @@ __device__ __forceinline__ void load_px(float2 (&z)[NC], const float2 *p)
     }
 }
 
+/* acc += w * v on both halves: one packed FP32x2 FMA (FFMA2 on sm_100a) */
+__device__ __forceinline__ void cfma2(float2 &acc, float w, float2 v)
+{
+    unsigned long long a = *reinterpret_cast<unsigned long long *>(&acc);
+    float2 ww = make_float2(w, w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(a)
+        : "l"(*reinterpret_cast<unsigned long long *>(&ww)), "l"(*reinterpret_cast<unsigned long long *>(&v)));
+    acc = *reinterpret_cast<float2 *>(&a);
+}
+
+/* Complex products as two packed FMAs each: a * b = a b.x + (-a.y, a.x) b.y and
+ * a * conj(b) = a b.x + (a.y, -a.x) b.y; the rotated operand is formed once per vector element. */
 template <int NC, bool HALF>
 __global__ void __launch_bounds__(128)
 walsh_small_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int nimg, int npatch)
@@ -104,16 +117,18 @@ walsh_small_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int 
         const int x0 = max(0, x - npatch), x1 = min(nimg - 1, x + npatch);
         const int y0 = max(0, y - npatch), y1 = min(nimg - 1, y + npatch);
         for (int px = x0; px <= x1; ++px)
-            for (int py = y0; py <= y1; ++py) {
-                float2 z[NC];
+            for (int py = y0; py <= y1; ++py) {         /* px outer, py inner: tron.cu:284-285 */
+                float2 z[NC], zr[NC];
                 load_px<NC>(z, src + ((size_t)px * nimg + py) * NC);
+#pragma unroll
+                for (int j = 0; j < NC; ++j) zr[j] = make_float2(z[j].y, -z[j].x);
                 int t = 0;
 #pragma unroll
                 for (int j = 0; j < NC; ++j)
 #pragma unroll
                     for (int k = j; k < NC; ++k, ++t) {
-                        float2 m = cmulc_(z[j], z[k]);
-                        A[t].x += m.x; A[t].y += m.y;
+                        if (k == j) A[t].x = fmaf(z[j].x, z[j].x, fmaf(z[j].y, z[j].y, A[t].x));
+                        else { cfma2(A[t], z[k].x, z[j]); cfma2(A[t], z[k].y, zr[j]); }   /* z_j conj(z_k) */
                     }
             }
         float2 xv[NC], yv[NC];
@@ -121,23 +136,25 @@ walsh_small_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int 
         for (int k = 0; k < NC; ++k) xv[k] = make_float2(1.f, 0.f);
 #pragma unroll 1
         for (int it = 0; it < 5; ++it) {                /* tron.cu:291 */
-            float nsq = 0.f;
+            float2 xr[NC];
+#pragma unroll
+            for (int k = 0; k < NC; ++k) xr[k] = make_float2(-xv[k].y, xv[k].x);
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < NC; ++k) {
+                for (int k = 0; k < NC; ++k) {          /* y_j += A[j][k] x_k, A[j][k] = conj(A[k][j]) for j > k */
                     const int lo = j < k ? j : k, hi = j < k ? k : j;
-                    float2 a = A[lo * NC - lo * (lo - 1) / 2 + (hi - lo)];
-                    if (j > k) a.y = -a.y;
-                    if (j == k) a.y = 0.f;
-                    float2 m = cmul_(a, xv[k]);
-                    acc.x += m.x; acc.y += m.y;
+                    const float2 a = A[lo * NC - lo * (lo - 1) / 2 + (hi - lo)];
+                    cfma2(acc, a.x, xv[k]);
+                    if (j < k) cfma2(acc, a.y, xr[k]);
+                    else if (j > k) cfma2(acc, -a.y, xr[k]);
                 }
                 yv[j] = acc;
             }
+            float nsq = 0.f;
 #pragma unroll
-            for (int k = 0; k < NC; ++k) nsq += yv[k].x * yv[k].x + yv[k].y * yv[k].y;
+            for (int k = 0; k < NC; ++k) nsq = fmaf(yv[k].x, yv[k].x, fmaf(yv[k].y, yv[k].y, nsq));
             const float inv = 1.0f / sqrtf(nsq);
 #pragma unroll
             for (int k = 0; k < NC; ++k) xv[k] = make_float2(yv[k].x * inv, yv[k].y * inv);
@@ -147,8 +164,8 @@ walsh_small_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int 
         float2 o = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {                  /* conj(x_c) z_c, tron.cu:294 */
-            float2 m = cmulc_(z[c], xv[c]);
-            o.x += m.x; o.y += m.y;
+            cfma2(o, xv[c].x, z[c]);
+            cfma2(o, xv[c].y, make_float2(z[c].y, -z[c].x));
         }
         store_px<HALF>(out, (size_t)blockIdx.y * npix + id, o);
     }
