@@ -268,3 +268,27 @@ def test_percoil_output_two_stage_fft_matches_radix8_and_rss(lib, monkeypatch, n
     assert rel_l2(coils, coils8) <= 2e-6
     assert rel_l2(np.sqrt((np.abs(coils.astype(np.complex128)) ** 2).sum(-1)), rss.real) <= 2e-6
     assert np.all(rss.imag == 0)
+
+
+def test_cli_walsh_and_cgnr_flags(lib, tmp_path):
+    """`tron -a -G ... -w 1` and `-i 2` write what the plan API computes (same 88-byte header as
+    the adjoint output of the reference CLI); `-i` without `-a` is refused with a message."""
+    import subprocess
+    import tron_b200 as t
+    torch_cuda()
+    dims = [4, 1, 64, 60, 1]
+    h_in = synth_complex((int(np.prod(dims)),), stream=67)
+    fin, fout = str(tmp_path / "in.ra"), str(tmp_path / "out.ra")
+    t.ra_write(fin, h_in, dims=dims)
+    base = ["-a", "-G", "-u", "0.5", "-d", "9"]
+    flags = dict(adjoint=True, golden=True, undersamp=0.5, prof_slide=9)
+    for extra, kw in ((["-w", "1"], dict(coil_combine=1, walsh_npatch=1)), (["-i", "2"], dict(niter=2)),
+                      (["-i", "1", "-w", "2"], dict(niter=1, coil_combine=1, walsh_npatch=2))):
+        subprocess.run([t.CLI_PATH] + base + extra + [fin, fout], check=True, timeout=300)
+        got, d, eltype, elbyte = t.ra_read(fout)
+        with t.Plan(t.make_config(dims, **flags, **kw)) as p:
+            want = p.recon_host(h_in)
+            assert d == [int(x) for x in p.geom.out_dims] and (eltype, elbyte) == (4, 8)
+        assert np.array_equal(got, want)
+    r = subprocess.run([t.CLI_PATH, "-i", "2", fin, fout], capture_output=True, text=True)
+    assert r.returncode == 1 and "CGNR" in r.stderr
