@@ -103,6 +103,27 @@ def test_pipeline_line_lengths_of_the_benchmarks(lib, reflib, dims, flags, radix
     assert rel_l2(got, want) <= TOL_F32, rel_l2(got, want)
 
 
+@pytest.mark.parametrize("ring", ["2", "5", "64"])
+def test_single_launch_fft_stage(lib, reflib, monkeypatch, ring):
+    """TRON_FFT_FUSED: both FFT passes in one launch, the intermediate in a ring of slices that stays in
+    L2; pass-B blocks wait on per-slice counters published by the pass-A blocks (fft.cu: p2w_adj_fused).
+    Same numbers as the two-launch stage, bit for bit, whatever the ring length."""
+    import tron_b200 as t
+    torch_cuda()
+    dims = [6, 1, 512, 150, 1]
+    flags = dict(adjoint=True, golden=True, undersamp=0.1, prof_slide=7)          # 15 slices of 51 spokes
+    h_in = synth_complex((int(np.prod(dims)),), stream=78)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        two = p.recon_host(h_in)
+    monkeypatch.setenv("TRON_FFT_FUSED", "1")
+    monkeypatch.setenv("TRON_FFT_RING", ring)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        one = p.recon_host(h_in)
+        assert p.last_launches() < 3 * p.geom.nz
+    assert np.array_equal(one, two)
+    assert rel_l2(one, run_ref(reflib, dims, flags, h_in)) <= TOL_F32
+
+
 def test_pipeline_more_than_six_coils(lib, reflib_wide):
     """nc > MAXCHAN needs the widened reference build (tron.h:51)."""
     import tron_b200 as t

@@ -732,20 +732,18 @@ __device__ __forceinline__ void p2w_stage2(float2 (&a)[N / R1], int b, const flo
 /* adjoint pass A: grid[plane][y][:] --FFT--> keep nkeep centre outputs --> tmp[plane][a][y].
  * The kept outputs are staged as F[line][a] (odd pitch) over the exchange buffer for the
  * transposed, coalesced store. */
-template <int N, int R1>
-__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 5)
-p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep,
-               int zero_r2)
+/* LD = 0: plain loads; 1: streaming loads (read once, evict first) */
+template <int N, int R1, int LD>
+__device__ __forceinline__ void p2w_pass_a_body(const float2 *__restrict__ grid_plane, float2 *__restrict__ tmp_plane,
+                                                const float2 *__restrict__ tw, int nkeep, int zero_r2, int y0,
+                                                float2 *smem)
 {
-    extern __shared__ float2 smem[];
     using G = P2W<N, R1>;
     const int l = threadIdx.x / G::T, j = threadIdx.x % G::T;
     float2 *xline = smem + l * G::LPX;
     float2 *F = smem;
     const int PF = G::fpitch(nkeep);
-    const int y0 = blockIdx.x * G::L;
-    const size_t plane = blockIdx.y;
-    const float2 *g = grid + plane * (size_t)N * N + (size_t)(y0 + l) * N + j;
+    const float2 *g = grid_plane + (size_t)(y0 + l) * N + j;
     {
         /* cells with X^2 + Y^2 > zero_r2 hold no sample (annulus of tron.cu:498-502 beyond nxos/2-1+W):
          * the gridding kernel does not store them and they are not fetched -- a fifth of the grid */
@@ -755,7 +753,7 @@ p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const 
 #pragma unroll
         for (int q = 0; q < R1; ++q) {
             const int X = X0 + q * G::T;
-            v[q] = X * X <= lim ? g[q * G::T] : make_float2(0.f, 0.f);
+            v[q] = X * X <= lim ? (LD ? __ldcs(g + q * G::T) : g[q * G::T]) : make_float2(0.f, 0.f);
         }
         p2w_stage1<N, R1, +1>(v, xline, j);
     }
@@ -777,40 +775,51 @@ p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const 
         }
     }
     __syncthreads();
-    float2 *out = tmp + plane * (size_t)nkeep * N + y0;
+    float2 *out = tmp_plane + y0;
     for (int idx = threadIdx.x; idx < nkeep * G::L; idx += G::THREADS) {
         const int aa = idx / G::L, ll = idx % G::L;
         out[(size_t)aa * N + ll] = F[ll * PF + aa];
     }
 }
 
+template <int N, int R1>
+__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 5)
+p2w_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep,
+               int zero_r2)
+{
+    extern __shared__ float2 smem[];
+    const size_t plane = blockIdx.y;
+    p2w_pass_a_body<N, R1, 0>(grid + plane * (size_t)N * N, tmp + plane * (size_t)nkeep * N, tw, nkeep, zero_r2,
+                              blockIdx.x * P2W<N, R1>::L, smem);
+}
+
 /* adjoint pass B for the usual 2x oversampling (nkeep = N/2), coils combined by sum of squares:
  * tmp[slice][ch][b][:] --FFT--> keep N/2 centre outputs, |.|^2 summed over the coils in registers
  * (a thread owns the same outputs for every coil), deapodised and stored once at the end.
  * mode 0: image = (sqrt(sum), 0) (tron.cu:255-268); mode 3: the partial sum itself (coil shards). */
-template <int N, int R1>
-__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 4)
-p2w_adj_pass_b_sos(const float2 *__restrict__ tmp, void *__restrict__ outv, const float *__restrict__ deapod,
-                   const float2 *__restrict__ tw, int nch, int mode, int half_out)
+/* LD = 0: plain loads; 1: ld.global.cg (L2 only): the fused kernel re-uses the intermediate's addresses for
+ * later slices, so a line of an earlier slice may still sit in this SM's (incoherent) L1 */
+template <int N, int R1, int LD>
+__device__ __forceinline__ void p2w_pass_b_sos_body(const float2 *__restrict__ tmp_slice, void *__restrict__ outv,
+                                                    size_t out_slice, const float *__restrict__ deapod,
+                                                    const float2 *__restrict__ tw, int nch, int mode, int half_out,
+                                                    int b0, float2 *smem)
 {
-    extern __shared__ float2 smem[];
     using G = P2W<N, R1>;
     constexpr int nkeep = N / 2, KT = G::R2 / 4;      /* kept k2: [0, KT) and [R2 - KT, R2) */
     const int l = threadIdx.x / G::T, j = threadIdx.x % G::T;
     float2 *xline = smem + l * G::LPX;
-    const int b0 = blockIdx.x * G::L;
-    const int slice = blockIdx.y;
     float acc[G::M2][2 * KT];
 #pragma unroll
     for (int m = 0; m < G::M2; ++m)
 #pragma unroll
         for (int u = 0; u < 2 * KT; ++u) acc[m][u] = 0.f;
-    const float2 *src = tmp + ((size_t)slice * nch * nkeep + b0 + l) * (size_t)N + j;
+    const float2 *src = tmp_slice + (size_t)(b0 + l) * (size_t)N + j;
     for (int ch = 0; ch < nch; ++ch) {
         {
             float2 v[R1];
 #pragma unroll
-            for (int q = 0; q < R1; ++q) v[q] = src[q * G::T];
+            for (int q = 0; q < R1; ++q) v[q] = LD ? __ldcg(src + q * G::T) : src[q * G::T];
             p2w_stage1<N, R1, +1>(v, xline, j);
         }
         src += (size_t)nkeep * N;
@@ -848,13 +857,79 @@ p2w_adj_pass_b_sos(const float2 *__restrict__ tmp, void *__restrict__ outv, cons
         const size_t pix = (size_t)aa * nkeep + b0 + ll;
         const float d = __ldg(deapod + pix);
         const float sum = S[ll * PS + aa] * d * d;
-        if (mode == 3) ((float *)outv)[(size_t)slice * img + pix] = sum;
+        if (mode == 3) ((float *)outv)[out_slice * img + pix] = sum;
         else {
             const float2 val = make_float2(sqrtf(sum), 0.f);              /* tron.cu:263-264 */
-            if (half_out) ((__half2 *)outv)[(size_t)slice * img + pix] = __float22half2_rn(val);
-            else ((float2 *)outv)[(size_t)slice * img + pix] = val;
+            if (half_out) ((__half2 *)outv)[out_slice * img + pix] = __float22half2_rn(val);
+            else ((float2 *)outv)[out_slice * img + pix] = val;
         }
     }
+}
+
+template <int N, int R1>
+__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 4)
+p2w_adj_pass_b_sos(const float2 *__restrict__ tmp, void *__restrict__ outv, const float *__restrict__ deapod,
+                   const float2 *__restrict__ tw, int nch, int mode, int half_out)
+{
+    extern __shared__ float2 smem[];
+    const int slice = blockIdx.y;
+    p2w_pass_b_sos_body<N, R1, 0>(tmp + (size_t)slice * nch * (N / 2) * (size_t)N, outv, (size_t)slice, deapod, tw, nch,
+                                  mode, half_out, blockIdx.x * P2W<N, R1>::L, smem);
+}
+
+/* Both passes in ONE launch, so that the intermediate never has to come back from HBM.
+ * Blocks are numbered slice by slice: the A blocks of slice s (nch planes x N/L row blocks), then the
+ * B blocks of slice s-1 (nkeep/L line blocks); the B blocks of the last slice close the grid.  A B block
+ * waits until the `ready` counter of its slice shows that every A block has published its rows
+ * (__threadfence + atomicAdd); all the blocks it waits for have lower indices, i.e. they were
+ * dispatched before it, so the wait cannot deadlock.  The intermediate is a ring of `ring` slices:
+ * slice s re-uses the slot of slice s - ring once that slice's B blocks have counted themselves `done`,
+ * so its 6.3 MB (cfg2) are overwritten while still in the 126 MB L2 and pass B reads them from L2
+ * (ld.global.cg: the SM's own L1 could hold the slot's previous contents).  Grid rows are fetched with
+ * streaming loads so that they do not push the ring out. */
+template <int N, int R1>
+__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 4)
+p2w_adj_fused(const float2 *__restrict__ grid, float2 *__restrict__ tmp, void *__restrict__ outv,
+              const float *__restrict__ deapod, const float2 *__restrict__ tw, int nch, int mode, int half_out,
+              int zero_r2, int nslices, int ring, int *__restrict__ ready, int *__restrict__ done)
+{
+    extern __shared__ float2 smem[];
+    using G = P2W<N, R1>;
+    constexpr int nkeep = N / 2, NA = N / G::L, NB = nkeep / G::L;
+    const int na = nch * NA, per = na + NB;
+    const int id = blockIdx.x;
+    int s = id / per, r = id - s * per;
+    const size_t slot_elems = (size_t)nch * nkeep * N;
+    if (s < nslices && r < na) {                          /* ---- pass A of slice s ---- */
+        if (s >= ring) {                                  /* the slot's previous reader must be finished */
+            if (threadIdx.x == 0) {
+                while (atomicAdd(done + s - ring, 0) < NB) __nanosleep(64);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        const int ch = r / NA, yb = r - ch * NA;
+        p2w_pass_a_body<N, R1, 1>(grid + ((size_t)s * nch + ch) * (size_t)N * N,
+                                  tmp + (size_t)(s % ring) * slot_elems + (size_t)ch * nkeep * N, tw, nkeep, zero_r2,
+                                  yb * G::L, smem);
+        __threadfence();                                  /* this thread's rows are visible device-wide ... */
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(ready + s, 1);    /* ... before the block counts itself */
+        return;
+    }
+    /* ---- pass B of slice s - 1 (of the last slice for the trailing blocks) ---- */
+    int bb;
+    if (s < nslices) { if (s == 0) return; bb = r - na; s -= 1; }
+    else { bb = id - nslices * per; s = nslices - 1; }
+    if (threadIdx.x == 0) {
+        while (atomicAdd(ready + s, 0) < na) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+    p2w_pass_b_sos_body<N, R1, 1>(tmp + (size_t)(s % ring) * slot_elems, outv, (size_t)s, deapod, tw, nch, mode,
+                                  half_out, bb * G::L, smem);
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(done + s, 1); }
 }
 
 /* adjoint pass B, nkeep = N/2, coils kept apart: mode 1 (single channel, complex image) and mode 2
@@ -923,6 +998,18 @@ template <int N, int R1> struct P2WLaunch {
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_a<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_b_sos<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N / 2)));
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_b_coil<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coil()));
+        TRON_CUDA(cudaFuncSetAttribute(p2w_adj_fused<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
+        return 0;
+    }
+    /* both passes in one launch (modes 0 / 3, nkeep = N/2); a.sync holds 2 * nslices zeroed counters */
+    static int adj_fused(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
+    {
+        const int per = a.nch * (N / G::L) + (N / 2) / G::L;
+        TRON_CUDA(cudaMemsetAsync(a.sync, 0, 2 * (size_t)a.nslices * sizeof(int), s));
+        p2w_adj_fused<N, R1><<<a.nslices * per + (N / 2) / G::L, G::THREADS, smem_a(N / 2), s>>>(
+            a.grid, a.tmp, a.out, a.deapod, f.tw, a.nch, a.mode, a.half_out, a.zero_r2, a.nslices, a.ring,
+            a.sync, a.sync + a.nslices);
+        TRON_CUDA(cudaGetLastError());
         return 0;
     }
     static size_t smem_coil() { return (size_t)(G::L * G::LPX + G::L * G::fpitch(N / 2)) * sizeof(float2); }
@@ -972,6 +1059,10 @@ template <int N, int L> struct P2Launch {
     {
         bool wide_a = false;
         if constexpr (P2WSplit<N>::R1 != 0) wide_a = getenv("TRON_FFT_R8") == nullptr;
+        if constexpr (P2WSplit<N>::R1 != 0) {
+            if (wide_a && a.sync && a.ring > 0 && 2 * f.nkeep == N && (a.mode == 0 || a.mode == 3))
+                return P2WLaunch<N, P2WSplit<N>::R1>::adj_fused(f, a, s);
+        }
         if (wide_a) {
             if constexpr (P2WSplit<N>::R1 != 0) { int rc = P2WLaunch<N, P2WSplit<N>::R1>::adj_a(f, a, s); if (rc) return rc; }
         } else {
@@ -1135,6 +1226,13 @@ int launch_adj_fft(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
                                               a.mode, a.half_out);
     TRON_CUDA(cudaGetLastError());
     return 0;
+}
+
+/* does launch_adj_fft run this launch as one kernel (p2w_adj_fused)? */
+bool adj_fft_single_launch(const FftPlan &f, const AdjFftLaunch &a)
+{
+    return f.pow2 && (f.n == 512 || f.n == 256) && getenv("TRON_FFT_R8") == nullptr && a.sync && a.ring > 0 &&
+           2 * f.nkeep == f.n && (a.mode == 0 || a.mode == 3);
 }
 
 int launch_fwd_fft(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)

@@ -137,6 +137,7 @@ static void plan_release(tron_plan *p)
     fft_plan_free(p->fft);
     cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->heavy_cells); cudaFree(p->grid_dbg);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_gridi); cudaFree(p->d_in); cudaFree(p->d_out);
+    cudaFree(p->fft_sync);
     cudaFree(p->d_coil); cudaFree(p->cg_r); cudaFree(p->cg_v); cudaFree(p->cg_z); cudaFree(p->cg_p); cudaFree(p->cg_part);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_in) cudaStreamDestroy(p->copy_in);
@@ -267,6 +268,17 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     p->overlap = cfg->adjoint && !p->percoil && p->nslices > p->batch && getenv("TRON_OVERLAP") != nullptr;   /* measured slower on B200: off */
     PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)(p->overlap ? 2 : 1) * p->batch * p->nch * n * n * sizeof(float2)));
     PLAN_CUDA(cudaMalloc(&p->d_tmp, (size_t)p->batch * p->nch * n * g.nx * sizeof(float2)));
+    if (cfg->adjoint && !p->percoil && !p->overlap && getenv("TRON_FFT_FUSED")) {
+        /* single-launch FFT stage (fft.cu: p2w_adj_fused): the intermediate lives in a ring of slices small
+         * enough for the L2.  Measured on cfg2: HBM traffic of the stage 1605 -> 715 MB per 64 slices, but
+         * 10.6-11.0 instead of 10.3 ms per step (the merged kernel is issue bound at 4 blocks/SM): off by default */
+        const size_t slot = (size_t)p->nch * n * g.nx * sizeof(float2);
+        int ring = getenv("TRON_FFT_RING") ? atoi(getenv("TRON_FFT_RING")) : (int)(((size_t)48 << 20) / (slot ? slot : 1));
+        if (ring < 2) ring = 2;
+        if (ring > p->batch) ring = p->batch;
+        p->fft_ring = ring;
+        PLAN_CUDA(cudaMalloc(&p->fft_sync, 2 * (size_t)p->batch * sizeof(int)));
+    }
     if (!cfg->adjoint && p->nch >= 32 && p->nch % 32 == 0)
         PLAN_CUDA(cudaMalloc(&p->d_gridi, (size_t)p->nch * n * n * sizeof(float2)));
     if (p->percoil) {
@@ -354,9 +366,10 @@ static int launch_batch_fft(tron_plan *p, void *d_out, const float2 *d_grid, int
     a.nslices = nb; a.nch = p->nch; a.nc_total = g.nc * g.nt; a.ch0 = g.coil_begin;
     a.mode = adjoint_mode(p); a.half_out = p->cfg.half_out;
     a.zero_r2 = p->zero_r2;
+    a.sync = p->fft_sync; a.ring = p->fft_ring;
     size_t per = (size_t)g.nx * g.ny * (a.mode == 2 ? (size_t)g.nc : 1);
     a.out = (char *)d_out + (size_t)z0 * per * p->out_elem_bytes;
-    p->last_launches += 2;
+    p->last_launches += adj_fft_single_launch(p->fft, a) ? 1 : 2;
     return launch_adj_fft(p->fft, a, s);
 }
 

@@ -99,8 +99,11 @@ struct AdjFftLaunch {
                                      3 partial sum of squares (float) */
     int half_out;
     int zero_r2 = 0x7fffffff;     /* grid cells with X^2 + Y^2 > zero_r2 are known to be zero and are not read */
+    int *sync = nullptr;          /* 2 * nslices counters: enables the single-launch path (fft.cu: p2w_adj_fused) */
+    int ring = 0;                 /* slices the intermediate `tmp` holds on that path (a ring of slots) */
 };
 int launch_adj_fft(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s);
+bool adj_fft_single_launch(const FftPlan &f, const AdjFftLaunch &a);
 
 struct FwdFftLaunch {
     const void *img;              /* [nx][nx][nc_total] channel-interleaved */
@@ -152,6 +155,7 @@ struct tron_plan {
     int nheavy = 0, heavy_r2 = -1;
     int zero_r2 = 0x7fffffff;            /* adjoint: cells beyond this squared radius never receive a sample */
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
+    int *fft_sync = nullptr; int fft_ring = 0;      /* single-launch FFT stage: counters, slices of d_tmp used as a ring */
     float2 *d_gridi = nullptr;                      /* forward, nc >= 32: channel-interleaved copy of the grid */
     float2 *d_coil = nullptr;                       /* per-coil images of a batch (Walsh combine, CGNR iterate x) */
     float2 *cg_r = nullptr, *cg_v = nullptr;        /* CGNR: residual and A p, [batch][npe1work][nro][nc] */
