@@ -292,3 +292,39 @@ def test_cli_walsh_and_cgnr_flags(lib, tmp_path):
         assert np.array_equal(got, want)
     r = subprocess.run([t.CLI_PATH, "-i", "2", fin, fout], capture_output=True, text=True)
     assert r.returncode == 1 and "CGNR" in r.stderr
+
+
+def _fuzz_percoil_cases(n, seed=77):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        nc = int(rng.choice([2, 4, 6, 8]))
+        nro = int(rng.choice([32, 48, 64]))
+        npe1work = int(rng.integers(8, 40))
+        nsl = int(rng.integers(1, 4))
+        slide = int(rng.integers(1, npe1work + 1)) if nsl > 1 else 0
+        dims = [nc, 1, nro, npe1work + (nsl - 1) * slide, 1]
+        flags = dict(adjoint=True, golden=bool(rng.integers(0, 2)), undersamp=(npe1work + 0.5) / nro,
+                     prof_slide=slide, skip_angles=int(rng.integers(0, 9)))
+        extra = dict(niter=int(rng.integers(0, 4)), coil_combine=int(rng.integers(0, 2)),
+                     walsh_npatch=int(rng.integers(0, 3)))
+        if extra["niter"] == 0 and extra["coil_combine"] == 0:
+            extra["coil_combine"] = 1
+        out.append((i, dims, flags, extra))
+    return out
+
+
+@pytest.mark.parametrize("i,dims,flags,extra", _fuzz_percoil_cases(12), ids=lambda v: str(v) if isinstance(v, int) else None)
+def test_fuzz_walsh_cgnr_vs_oracle(lib, oracle, reflib, i, dims, flags, extra):
+    """Seeded random geometries through -i / -w (any mix) against the oracle's restatement."""
+    import tron_b200 as t
+    torch_cuda()
+    h_in = synth_complex((int(np.prod(dims)),), stream=600 + i)
+    cfg = oracle.config(dims, True, golden=flags["golden"], undersamp=flags["undersamp"], prof_slide=flags["prof_slide"],
+                        skip_angles=flags["skip_angles"], **extra)
+    install_trig(oracle, reflib, cfg, flags["golden"], flags["skip_angles"])
+    want = oracle.recon(cfg, h_in)
+    oracle.set_trig_table(None)
+    with t.Plan(t.make_config(dims, **flags, **extra)) as p:
+        got = p.recon_host(h_in)
+    assert rel_l2(got, want) <= (1e-4 if extra["niter"] else TOL_F32), (dims, flags, extra, rel_l2(got, want))

@@ -556,3 +556,53 @@ def test_shepp_logan_round_trip(lib, reflib):
             rec = np.abs(img.reshape(256, 256)); ref_ph = np.abs(ph)
             c = np.corrcoef(rec.ravel(), ref_ph.ravel())[0, 1]
             assert c > 0.95, c
+
+
+def _fuzz_cases(n, seed=20261017):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        adjoint = bool(rng.integers(0, 4) > 0)
+        nc = int(rng.choice([1, 2, 4, 6]))
+        golden = bool(rng.integers(0, 2))
+        W = float(rng.choice([2.0, 2.0, 2.5, 3.0, 4.0]))
+        gridos = float(rng.choice([2.0, 2.0, 2.0, 1.5, 1.25]))
+        if adjoint:
+            nro = int(rng.choice([32, 48, 64, 96, 128, 160, 256]))
+            npe1work = int(rng.integers(3, 90))
+            undersamp = (npe1work + 0.5) / nro
+            nslide = int(rng.integers(1, 5))
+            slide = int(rng.integers(1, npe1work + 1)) if nslide > 1 else 0
+            npe1 = npe1work + (nslide - 1) * slide + int(rng.integers(0, max(slide, 1)))
+            skip = int(rng.integers(0, 50))
+            if int(nro / 2 * gridos) % 2:          # the reference's 4x4 cell remap needs nxos % 4 == 0
+                gridos = 2.0
+            if int(nro / 2 * gridos) % 4:
+                gridos = 2.0
+            dims = [nc, 1, nro, npe1, 1]
+            flags = dict(adjoint=True, golden=golden, kernwidth=W, gridos=gridos, undersamp=undersamp,
+                         prof_slide=slide, skip_angles=skip)
+        else:
+            nx = int(rng.choice([16, 24, 32, 48, 64, 100]))
+            if int(nx * gridos) % 4:
+                gridos = 2.0
+            dims = [nc, 1, nx, nx, 1]
+            flags = dict(adjoint=False, golden=golden, kernwidth=W, gridos=gridos,
+                         undersamp=float(rng.choice([1.0, 0.5, 0.3])), skip_angles=int(rng.integers(0, 20)))
+        out.append((i, dims, flags))
+    return out
+
+
+@pytest.mark.parametrize("i,dims,flags", _fuzz_cases(40), ids=lambda v: str(v) if isinstance(v, int) else None)
+def test_fuzz_pipeline_vs_reference(lib, reflib, i, dims, flags):
+    """Seeded random geometries (channel counts, line lengths incl. non-powers of two, kernel widths,
+    oversampling ratios, sliding windows with ragged tails, skip offsets) against the reference itself."""
+    import tron_b200 as t
+    torch_cuda()
+    h_in = synth_complex((int(np.prod(dims)),), stream=500 + i)
+    want = run_ref(reflib, dims, flags, h_in)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        assert [int(x) for x in p.geom.out_dims] == reflib.out_dims
+        got = p.recon_host(h_in)
+    assert got.shape == want.shape
+    assert rel_l2(got, want) <= TOL_F32, (dims, flags, rel_l2(got, want))
