@@ -446,7 +446,7 @@ void oracle_coilcombinesos(ocplx *img, const ocplx *coilimg, int nimg, int nchan
  * reciprocal (float2math.h:24-28); img = sum_c conj(x_c) * z_c.  The reference
  * zeroes NCHAN*NCHAN = 36 entries whatever nchan is (tron.cu:282, tron.h:50), so
  * it is only defined for nchan <= 6; this restatement zeroes nchan^2.  A patch of
- * all zeros gives 0 * (1/0) = NaN in the reference and here. */
+ * all zeros gives 0 * (1/0) = NaN in the reference; here (and in the product) it gives 0. */
 void oracle_coilcombinewalsh(ocplx *img, const ocplx *coilimg, int nimg, int nchan, int npatch)
 {
     if (nchan == 1) { memcpy(img, coilimg, sizeof(ocplx) * (size_t)nimg * nimg); return; }
@@ -482,7 +482,7 @@ void oracle_coilcombinewalsh(ocplx *img, const ocplx *coilimg, int nimg, int nch
                     }
                 }
                 for (int k = 0; k < nchan; ++k) nsq += y[k].x * y[k].x + y[k].y * y[k].y;
-                float inv = 1.0f / sqrtf(nsq);
+                float inv = nsq > 0.f ? 1.0f / sqrtf(nsq) : 0.f;   /* the reference: NaN for a patch of zeros */
                 for (int k = 0; k < nchan; ++k) { x[k].x = y[k].x * inv; x[k].y = y[k].y * inv; }
             }
             ocplx o = {0.f, 0.f};

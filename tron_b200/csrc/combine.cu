@@ -21,7 +21,8 @@
  *       pixel and iteration -- 2 nc (2p+1)^2 complex FMAs per iteration instead of nc^2 plus the
  *       nc^2 (2p+1)^2 of forming A, and no nc^2 storage (the reference keeps A in local memory
  *       and is limited to MAXCHAN = 6).
- * A patch of zeros gives 0 * (1/0) = NaN, as in the reference.
+ * A patch of zeros (e.g. the image row/column the CGNR iteration clears) gives 0 here; the reference would
+ * produce 0 * (1/0) = NaN there.
  */
 #include "tron_internal.h"
 
@@ -155,7 +156,7 @@ walsh_small_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int 
             float nsq = 0.f;
 #pragma unroll
             for (int k = 0; k < NC; ++k) nsq = fmaf(yv[k].x, yv[k].x, fmaf(yv[k].y, yv[k].y, nsq));
-            const float inv = 1.0f / sqrtf(nsq);
+            const float inv = nsq > 0.f ? 1.0f / sqrtf(nsq) : 0.f;
 #pragma unroll
             for (int k = 0; k < NC; ++k) xv[k] = make_float2(yv[k].x * inv, yv[k].y * inv);
         }
@@ -237,7 +238,7 @@ walsh_wide_kernel(void *__restrict__ out, const float2 *__restrict__ coil, int n
 #pragma unroll
             for (int i = 0; i < CPL; ++i) nsq += yv[i].x * yv[i].x + yv[i].y * yv[i].y;
             nsq = warp_sum(nsq);
-            const float inv = 1.0f / sqrtf(nsq);
+            const float inv = nsq > 0.f ? 1.0f / sqrtf(nsq) : 0.f;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) xv[i] = make_float2(yv[i].x * inv, yv[i].y * inv);
         }
