@@ -113,8 +113,10 @@ __device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], WideLis
     __syncwarp();
 }
 
+/* one channel chunk, one slice per group (cfg3): 4 CTAs/SM (64 registers, 26 words of spill) measured 8 % faster
+ * than 2 (128 registers); the wider instantiations spill too much below 128 registers (cfg5: 3 CTAs/SM 35 % slower) */
 template <int LPC, int NCHUNK, int GS, bool HALF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NCHUNK == 1 && GS == 1) ? 4 : 2)
 grid_wide_kernel(const GridLaunch g)
 {
     __shared__ WideList lists[8];
