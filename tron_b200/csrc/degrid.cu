@@ -44,6 +44,14 @@ __device__ __forceinline__ void store_sample(void *samples, size_t idx, const fl
     }
 }
 
+/* (u + n) % n of tron.cu:569-570 for -n <= u < 2n (taps reach at most W < n cells past the grid):
+ * two selects instead of an integer division */
+__device__ __forceinline__ int wrap_cell(int u, int n)
+{
+    u += u < 0 ? n : 0;
+    return u - (u >= n ? n : 0);
+}
+
 template <int CH, bool HALF, int NT>
 __global__ void __launch_bounds__(256)
 degrid_gather_kernel(const DegridLaunch d)
@@ -84,7 +92,7 @@ degrid_gather_kernel(const DegridLaunch d)
             float dy = (float)yu - Y;
             bool in = ((float)yu <= ytop) && (fabsf(dy) < W);
             wy[k] = in ? kb_weight(dy, d.kb) : 0.f;
-            jy[k] = (yu + n) % n;
+            jy[k] = wrap_cell(yu, n);
         }
         const int ntapy = min(NT, (int)floorf(ytop) - yu0 + 1);
 
@@ -98,7 +106,7 @@ degrid_gather_kernel(const DegridLaunch d)
             float dx = (float)xu - X;
             if (!(fabsf(dx) < W)) continue;
             const float wx = kb_weight(dx, d.kb);
-            const float2 *row = g0 + (size_t)((xu + n) % n) * n;
+            const float2 *row = g0 + (size_t)wrap_cell(xu, n) * n;
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
                 if (k < ntapy) {
