@@ -152,6 +152,8 @@ static void plan_release(tron_plan *p)
     delete p;
 }
 
+#define HOST_BATCH_MAX 64
+
 static int pick_batch(const tron_plan *p)
 {
     if (p->cfg.batch_slices > 0) return p->cfg.batch_slices < p->nslices ? p->cfg.batch_slices : p->nslices;
@@ -161,10 +163,12 @@ static int pick_batch(const tron_plan *p)
     if (p->percoil) per += (size_t)p->g.nc * p->g.nx * p->g.nx * sizeof(float2);
     if (p->cfg.niter > 0) per += 2 * (size_t)p->g.nc * ((size_t)p->g.nx * p->g.nx + (size_t)p->g.nro * p->g.npe1work) * sizeof(float2);
     /* launches of >= 32 slices reach the kernels' asymptotic throughput (profiles/r01_grid_only_timing.txt);
-     * the work buffers are bounded to ~1.5 GB of the 180 GB */
-    size_t b = ((size_t)1536 << 20) / (per ? per : 1);
+     * longer launches still shave the drain of each kernel (measured on cfg2, device resident: 10.31 ms per
+     * step at 64 slices per launch, 10.02 at 128); the work buffers are bounded to ~6 GB of the 180 GB.
+     * The host pipeline caps its launches at HOST_BATCH_MAX (copy/compute overlap wants them shorter). */
+    size_t b = ((size_t)6144 << 20) / (per ? per : 1);
     if (b < 1) b = 1;
-    if (b > 64) b = 64;
+    if (b > 256) b = 256;
     if ((int)b > p->nslices) b = p->nslices;
     return (int)b;
 }
@@ -416,13 +420,15 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     const int gs = p->tabs.gs > 0 ? p->tabs.gs : 1;
     for (int z0 = 0, nb = 0; z0 < p->nslices; z0 += nb, i ^= 1) {
         nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
-        if (host && p->batch >= 8 * gs) {
+        const int hb = host ? (p->batch < HOST_BATCH_MAX ? p->batch : (HOST_BATCH_MAX / gs) * gs) : p->batch;
+        if (host && nb > hb) nb = hb;
+        if (host && hb >= 8 * gs) {
             /* host mode ramps the batch size up at the start and down at the end, so that the first
              * upload and the last download (which nothing overlaps) are short */
-            int ramp = p->batch;
-            if (z0 < p->batch) ramp = z0 == 0 ? p->batch / 8 : (z0 < p->batch / 2 ? p->batch / 4 : p->batch / 2);
+            int ramp = hb;
+            if (z0 < hb) ramp = z0 == 0 ? hb / 8 : (z0 < hb / 2 ? hb / 4 : hb / 2);
             const int rem = p->nslices - z0;
-            if (rem <= p->batch) ramp = rem > p->batch / 4 ? rem / 2 : rem;
+            if (rem <= hb) ramp = rem > hb / 4 ? rem / 2 : rem;
             ramp = ((ramp + gs - 1) / gs) * gs;
             if (ramp >= gs && ramp < nb) nb = ramp;
         }
