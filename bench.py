@@ -223,7 +223,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (gridding), timed alone on this stream
     n, nc = g["nxos"], g["nc"]
-    B = min(32, g["nz"])
+    B = min(256, g["nz"])                                          # the launch length the device pipeline uses
     d_grid = torch.empty(B * nc * n * n * 2, dtype=torch.float32, device="cuda")
     nlaunch = 0
     for z0 in range(0, min(g["nz"], 4 * B), B):                     # warm-up
