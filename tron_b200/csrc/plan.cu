@@ -418,6 +418,14 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     size_t spokes_up = 0;
     int i = 0;
     const int gs = p->tabs.gs > 0 ? p->tabs.gs : 1;
+    /* TRON_HOST_TRACE: when did the last upload, the last kernel and the last download finish? */
+    static const bool trace = getenv("TRON_HOST_TRACE") != nullptr;
+    cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace && host) {
+        for (int k = 0; k < 4; ++k) cudaEventCreate(&tr[k]);
+        cudaDeviceSynchronize();
+        cudaEventRecord(tr[0], p->copy_in);
+    }
     for (int z0 = 0, nb = 0; z0 < p->nslices; z0 += nb, i ^= 1) {
         nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
         const int hb = host ? (p->batch < HOST_BATCH_MAX ? p->batch : (HOST_BATCH_MAX / gs) * gs) : p->batch;
@@ -475,9 +483,16 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
         }
     }
     if (host) {
+        if (trace) { cudaEventRecord(tr[1], p->copy_in); cudaEventRecord(tr[2], sf); cudaEventRecord(tr[3], p->copy_out); }
         TRON_CUDA(cudaStreamSynchronize(p->copy_out));
         TRON_CUDA(cudaStreamSynchronize(sf));
         TRON_CUDA(cudaStreamSynchronize(sg));
+        if (trace) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tr[0], tr[1]); cudaEventElapsedTime(&b, tr[0], tr[2]); cudaEventElapsedTime(&c, tr[0], tr[3]);
+            fprintf(stderr, "tron host trace: uploads done %.3f ms, kernels done %.3f ms, downloads done %.3f ms\n", a, b, c);
+            for (int k = 0; k < 4; ++k) cudaEventDestroy(tr[k]);
+        }
     } else if (overlap) {
         TRON_CUDA(cudaEventRecord(p->ev_user, sf));
         TRON_CUDA(cudaStreamWaitEvent(user, p->ev_user, 0));
