@@ -341,3 +341,39 @@ def test_fuzz_walsh_cgnr_vs_oracle(lib, oracle, reflib, i, dims, flags, extra):
         assert rel_l2(np.abs(got), np.abs(want)) <= 2e-4 and rel_l2(got, want) <= 1e-3, (dims, flags, extra)
     else:
         assert rel_l2(got, want) <= (1e-4 if extra["niter"] else TOL_F32), (dims, flags, extra, rel_l2(got, want))
+
+
+def test_walsh_and_cgnr_with_fp16_output(lib):
+    """-H (complex-half output) after the Walsh combine and after CGNR + RSS: the float result rounded once."""
+    import tron_b200 as t
+    torch_cuda()
+    dims = [6, 1, 64, 70, 1]
+    flags = dict(adjoint=True, golden=True, undersamp=0.4, prof_slide=11)
+    h_in = synth_complex((int(np.prod(dims)),), stream=68)
+    for extra in (dict(coil_combine=1, walsh_npatch=1), dict(niter=2), dict(niter=1, coil_combine=1, walsh_npatch=2)):
+        with t.Plan(t.make_config(dims, **flags, **extra)) as p:
+            full = p.recon_host(h_in)
+        with t.Plan(t.make_config(dims, half_out=True, **flags, **extra)) as p:
+            half = p.recon_host(h_in)
+        assert half.dtype == np.float16 and half.shape == (full.size, 2)
+        want = full.view(np.float32).reshape(-1, 2).astype(np.float16)
+        assert np.array_equal(half, want), extra
+
+
+def test_cgnr_single_coil_complex_output(lib, oracle, reflib):
+    """nc = 1: the iterate passes through as a complex image (tron.cu:265-266), with or without -w."""
+    import tron_b200 as t
+    torch_cuda()
+    dims = [1, 1, 64, 40, 1]
+    flags = dict(adjoint=True, golden=True, undersamp=0.5, prof_slide=4, skip_angles=2)
+    h_in = synth_complex((int(np.prod(dims)),), stream=69)
+    cfg = oracle.config(dims, True, golden=True, undersamp=0.5, prof_slide=4, skip_angles=2, niter=3)
+    install_trig(oracle, reflib, cfg, True, 2)
+    want = oracle.recon(cfg, h_in)
+    oracle.set_trig_table(None)
+    with t.Plan(t.make_config(dims, niter=3, **flags)) as p:
+        got = p.recon_host(h_in)
+    with t.Plan(t.make_config(dims, niter=3, coil_combine=1, walsh_npatch=1, **flags)) as p:
+        got_w = p.recon_host(h_in)
+    assert np.abs(got.imag).max() > 0 and rel_l2(got, want) <= 1e-4
+    assert np.array_equal(got, got_w)
