@@ -124,7 +124,10 @@ grid_wide_kernel(const GridLaunch g)
     WideList &L = lists[warp];
     const int n = g.n;
     const int tiles_x = (n + 15) >> 4;
-    const int rank = blockIdx.x / g.ngroups, grp = blockIdx.x - rank * g.ngroups;
+    /* a CTA takes a quarter of a 16 x 16 tile (8 blocks of 4 x 2 cells, one per warp): with a single slice in
+     * flight (cfg5) whole-tile CTAs near DC ran 100x longer than the average and a third of the SM time was tail */
+    const int unit = blockIdx.x / g.ngroups, grp = blockIdx.x - unit * g.ngroups;
+    const int rank = unit >> 2, quarter = unit & 3;
     const int tile = __ldg(g.tile_order + rank);
     const int ty = tile >> 16, tx = tile & 0xffff;
     const int chan0 = blockIdx.y * (LPC * NCHUNK);           /* first plan-local channel of this CTA */
@@ -143,7 +146,7 @@ grid_wide_kernel(const GridLaunch g)
     const float Rmaxf = (float)(n / 2 - 1);
     const float lut_scale = (float)g.nbins / PI_F;
 
-    for (int bi = warp; bi < 32; bi += 8) {
+    for (int bi = quarter * 8 + warp; bi < quarter * 8 + 8; bi += 8) {
         const int x0 = tx * 16 + (bi & 3) * 4, y0 = ty * 16 + (bi >> 2) * 2;
         if (x0 >= n || y0 >= n) continue;
         const int X0 = x0 - n / 2, Y0 = y0 - n / 2;
@@ -317,7 +320,7 @@ static int launch_wide(GridLaunch g, cudaStream_t s)
     int tiles = ((g.n + 15) / 16) * ((g.n + 15) / 16);
     g.ngroups = (g.z0 + g.nslices - 1) / GS - g.z0 / GS + 1;
     int per_cta = LPC * NCHUNK;
-    dim3 grid(tiles * g.ngroups, (g.nch + per_cta - 1) / per_cta);
+    dim3 grid(tiles * 4 * g.ngroups, (g.nch + per_cta - 1) / per_cta);
     if (g.half_in) grid_wide_kernel<LPC, NCHUNK, GS, true><<<grid, 256, 0, s>>>(g);
     else           grid_wide_kernel<LPC, NCHUNK, GS, false><<<grid, 256, 0, s>>>(g);
     TRON_CUDA(cudaGetLastError());
