@@ -166,7 +166,9 @@ static int pick_batch(const tron_plan *p)
      * longer launches still shave the drain of each kernel (measured on cfg2, device resident: 10.31 ms per
      * step at 64 slices per launch, 10.02 at 128); the work buffers are bounded to ~6 GB of the 180 GB.
      * The host pipeline caps its launches at HOST_BATCH_MAX (copy/compute overlap wants them shorter). */
-    size_t b = ((size_t)6144 << 20) / (per ? per : 1);
+    size_t budget = (size_t)6144 << 20, freeb = 0, totalb = 0;
+    if (cudaMemGetInfo(&freeb, &totalb) == cudaSuccess && freeb / 3 < budget) budget = freeb / 3;   /* shared GPUs */
+    size_t b = budget / (per ? per : 1);
     if (b < 1) b = 1;
     if (b > 256) b = 256;
     if ((int)b > p->nslices) b = p->nslices;
