@@ -30,6 +30,8 @@ namespace tronb {
 struct __align__(16) DwWeights {
     float4 wx[DW_MAXU];   /* row factor of samples 0..3 */
     float4 wy[DW_MAXU];   /* column factor */
+    float4 wp[DW_MAXU];   /* wx[i] * wy[j] of the current row: formed once per row by lanes j < nuy, so the
+                             channel loop reads the finished tap weight instead of multiplying per cell */
     int coff[DW_MAXU + 4];/* element offset of every column of the union window: the periodic wrap is applied once
                              per column here instead of an integer modulo per cell (ncu: 45 -> 25 instructions per
                              cell, cfg5 forward 18.4 -> 13.6 ms); padded by repeating the last column */
@@ -117,6 +119,12 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
             for (int s = 0; s < DW_S; ++s) acc[c][s] = make_float2(0.f, 0.f);
         for (int i = 0; i < nux; ++i) {
             const float4 a = S.wx[i];
+            __syncwarp();
+            if (lane < nuy) {
+                const float4 b = S.wy[lane];
+                S.wp[lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+            }
+            __syncwarp();
             const int row = (xlo + i + n) % n;                              /* periodic, tron.cu:569 */
             const float2 *grow = gi + ((size_t)row * n) * nch + chan0 + lane;
             for (int j0 = 0; j0 < nuy; j0 += 4) {
@@ -130,8 +138,8 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     if (j0 + jj < nuy) {
-                        const float4 b = S.wy[j0 + jj];
-                        const float w0 = a.x * b.x, w1 = a.y * b.y, w2 = a.z * b.z, w3 = a.w * b.w;
+                        const float4 b = S.wp[j0 + jj];
+                        const float w0 = b.x, w1 = b.y, w2 = b.z, w3 = b.w;
 #pragma unroll
                         for (int c = 0; c < NCHUNK; ++c) {
                             ffma2d(acc[c][0], w0, v[jj][c]); ffma2d(acc[c][1], w1, v[jj][c]);
