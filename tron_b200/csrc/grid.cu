@@ -425,7 +425,7 @@ __device__ __forceinline__ void store_cell(const GridLaunch &g, const float2 (&a
         if (zl0 + s >= 0 && zl0 + s < g.nslices) {
             float2 *o = out;
 #pragma unroll
-            for (int i = 0; i < CH; ++i) { *o = acc[s][i]; o += plane; }
+            for (int i = 0; i < CH; ++i) { __stcs(o, acc[s][i]); o += plane; }   /* streaming: keep the samples in L2 */
         }
         out += slice_stride;
     }
