@@ -106,11 +106,36 @@ class ClockSampler:
                 "samples": len(rows)}
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are
+    allocated (first touch places them on that node): with several ranks per box the host<->device copies of
+    the end-to-end leg otherwise cross sockets.  Best effort: returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def dist_setup(n_gpus):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    bind_to_gpu_numa(local)
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
