@@ -171,10 +171,14 @@ int build_tile_order(int **d_order, int n, int th)
 }
 
 /* Cells with X^2 + Y^2 <= r2 are "heavy": their spoke window holds about
- * HEAVY_SPOKES or more spokes.  Returns the list (packed y<<16 | x, nearest DC first). */
-int build_heavy_cells(int **d_cells, int *nheavy, int *heavy_r2, int n, int npe, float W)
+ * HEAVY_SPOKES or more spokes.  The warp-per-cell path exists to keep the cells next to DC (which see every
+ * spoke) off the critical path of a launch; it costs a 48-register shuffle reduction per cell, so the
+ * threshold follows the size of the launch: 24 spokes when a launch is small (one 512^2 slice: 31 vs 76 us
+ * with 96), 96 when there is enough other work to hide the long cells (cfg2 at 64+ slices per launch:
+ * 5.8 vs 6.2 us/slice with 24; cfg5 8-coil shard, 2048^2: 3.3 vs 4.4 ms).  Returns the list (packed y<<16 | x, nearest DC first). */
+int build_heavy_cells(int **d_cells, int *nheavy, int *heavy_r2, int n, int npe, float W, int heavy_spokes)
 {
-    const int HEAVY_SPOKES = 24;
+    const int HEAVY_SPOKES = getenv("TRON_HEAVY") ? atoi(getenv("TRON_HEAVY")) : heavy_spokes;
     *d_cells = nullptr; *nheavy = 0; *heavy_r2 = -1;
     double arg = HEAVY_SPOKES * 3.14159265358979323846 / (2.0 * npe);
     if (arg >= 1.2) return 0;                              /* too few spokes for any cell to be heavy */
@@ -537,6 +541,10 @@ template <int CH, int GS>
 static int launch_grid_cg(GridLaunch g, cudaStream_t s)
 {
     g.ngroups = (g.z0 + g.nslices - 1) / GS - g.z0 / GS + 1;
+    if ((double)g.n * g.n * g.ngroups >= 2.0e6) {
+        /* enough cell-groups in flight to hide the long cells: only the innermost ones take the warp path */
+        g.heavy_cells = g.heavy_cells_big; g.nheavy = g.nheavy_big; g.heavy_r2 = g.heavy_r2_big;
+    }
     const bool plain = g.kb.fast && g.nro == g.n;
     if (g.half_in) return plain ? launch_grid_cghp<CH, GS, true, true>(g, s) : launch_grid_cghp<CH, GS, true, false>(g, s);
     return plain ? launch_grid_cghp<CH, GS, false, true>(g, s) : launch_grid_cghp<CH, GS, false, false>(g, s);

@@ -135,7 +135,7 @@ static void plan_release(tron_plan *p)
     if (!p) return;
     cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.gx); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
     fft_plan_free(p->fft);
-    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->heavy_cells); cudaFree(p->grid_dbg);
+    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->heavy_cells); cudaFree(p->heavy_cells_big); cudaFree(p->grid_dbg);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_gridi); cudaFree(p->d_in); cudaFree(p->d_out);
     cudaFree(p->fft_sync);
     cudaFree(p->d_coil); cudaFree(p->cg_r); cudaFree(p->cg_v); cudaFree(p->cg_z); cudaFree(p->cg_p); cudaFree(p->cg_part);
@@ -256,7 +256,10 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     if (cfg->adjoint) {
         PLAN_TRY(build_tile_order(&p->tile_order, n, 16));
         PLAN_TRY(build_tile_order(&p->tile_order8, n, 8));
-        PLAN_TRY(build_heavy_cells(&p->heavy_cells, &p->nheavy, &p->heavy_r2, n, p->tabs.npe, cfg->kernwidth));
+        /* two heavy-cell lists: launches with little other work need more of the DC neighbourhood on the
+         * warp-per-cell path than long ones (grid.cu: build_heavy_cells, launch_grid_cg picks per launch) */
+        PLAN_TRY(build_heavy_cells(&p->heavy_cells, &p->nheavy, &p->heavy_r2, n, p->tabs.npe, cfg->kernwidth, 24));
+        PLAN_TRY(build_heavy_cells(&p->heavy_cells_big, &p->nheavy_big, &p->heavy_r2_big, n, p->tabs.npe, cfg->kernwidth, 96));
     }
     PLAN_CUDA(cudaMalloc(&p->deapod_adj, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_CUDA(cudaMalloc(&p->deapod_fwd, (size_t)g.nx * g.nx * sizeof(float)));
@@ -330,6 +333,7 @@ GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d
     L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.tab_gx = p->tabs.gx; L.lut = p->tabs.lut; L.cells = p->tabs.cells;
     L.tile_order = p->tile_order; L.tile_order8 = p->tile_order8;
     L.heavy_cells = p->heavy_cells; L.nheavy = p->nheavy; L.heavy_r2 = p->heavy_r2;
+    L.heavy_cells_big = p->heavy_cells_big; L.nheavy_big = p->nheavy_big; L.heavy_r2_big = p->heavy_r2_big;
     L.tab_per_slice = p->tabs.ntab > 1 ? 1 : 0;
     L.nbins = p->tabs.nbins;
     L.n = g.nxos; L.nro = g.nro; L.npe = p->tabs.npe; L.gs = p->tabs.gs; L.ngroups = 0;
