@@ -135,7 +135,7 @@ static void plan_release(tron_plan *p)
     if (!p) return;
     cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.gx); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
     fft_plan_free(p->fft);
-    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->heavy_cells); cudaFree(p->heavy_cells_big); cudaFree(p->grid_dbg);
+    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->tile_order_rows); cudaFree(p->tile_order8_rows); cudaFree(p->heavy_cells); cudaFree(p->heavy_cells_big); cudaFree(p->grid_dbg);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_gridi); cudaFree(p->d_in); cudaFree(p->d_out);
     cudaFree(p->fft_sync);
     cudaFree(p->d_coil); cudaFree(p->cg_r); cudaFree(p->cg_v); cudaFree(p->cg_z); cudaFree(p->cg_p); cudaFree(p->cg_part);
@@ -254,8 +254,10 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         p->zero_r2 = r2 < 2.0e9 ? (int)r2 : 0x7fffffff;
     }
     if (cfg->adjoint) {
-        PLAN_TRY(build_tile_order(&p->tile_order, n, 16));
-        PLAN_TRY(build_tile_order(&p->tile_order8, n, 8));
+        PLAN_TRY(build_tile_order(&p->tile_order, n, 16, false));
+        PLAN_TRY(build_tile_order(&p->tile_order8, n, 8, false));
+        PLAN_TRY(build_tile_order(&p->tile_order_rows, n, 16, true));
+        PLAN_TRY(build_tile_order(&p->tile_order8_rows, n, 8, true));
         /* two heavy-cell lists: launches with little other work need more of the DC neighbourhood on the
          * warp-per-cell path than long ones (grid.cu: build_heavy_cells, launch_grid_cg picks per launch) */
         PLAN_TRY(build_heavy_cells(&p->heavy_cells, &p->nheavy, &p->heavy_r2, n, p->tabs.npe, cfg->kernwidth, 24));
@@ -332,6 +334,7 @@ GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d
     L.samples = d_samples; L.grid = d_grid;
     L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.tab_gx = p->tabs.gx; L.lut = p->tabs.lut; L.cells = p->tabs.cells;
     L.tile_order = p->tile_order; L.tile_order8 = p->tile_order8;
+    L.tile_order_rows = p->tile_order_rows; L.tile_order8_rows = p->tile_order8_rows;
     L.heavy_cells = p->heavy_cells; L.nheavy = p->nheavy; L.heavy_r2 = p->heavy_r2;
     L.heavy_cells_big = p->heavy_cells_big; L.nheavy_big = p->nheavy_big; L.heavy_r2_big = p->heavy_r2_big;
     L.tab_per_slice = p->tabs.ntab > 1 ? 1 : 0;

@@ -36,6 +36,7 @@ struct GridLaunch {               /* everything the gridding kernel needs */
     const float4 *tab_cs; const int *tab_pe; const float4 *tab_gx; const int *lut; const int2 *cells;
     const int *tile_order;        /* [tiles] 16x16 tiles, heaviest (nearest DC) first */
     const int *tile_order8;       /* same for 16x8 tiles (128-thread blocks) */
+    const int *tile_order_rows, *tile_order8_rows;   /* both lists row by row (long launches) */
     const int *heavy_cells; int nheavy; int heavy_r2;   /* cells with X^2+Y^2 <= heavy_r2: one warp each */
     const int *heavy_cells_big; int nheavy_big; int heavy_r2_big;   /* the shorter list for launches with much other work */
     int tab_per_slice;            /* 1: table index = slice group, 0: shared */
@@ -72,7 +73,7 @@ bool degrid_wide_applicable(const DegridLaunch &d);
 int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s);
 int launch_build_tables(SpokeTables &t, int npe, int npe_formula, int ntab, int tab_stride, int skip, int golden,
                         int adjoint, int win, int slide, int gs, int nslices, int n, float W, cudaStream_t s);
-int build_tile_order(int **d_order, int n, int th);
+int build_tile_order(int **d_order, int n, int th, bool raster);
 int build_heavy_cells(int **d_cells, int *nheavy, int *heavy_r2, int n, int npe, float W, int heavy_spokes);
 int launch_interleave(float2 *dst, const float2 *planar, int nch, int n, int nslices, cudaStream_t s);
 int launch_deinterleave(float2 *planar, const float2 *src, int nch, int n, cudaStream_t s);
@@ -152,6 +153,7 @@ struct tron_plan {
     tronb::FftPlan fft;
     float *deapod_adj = nullptr, *deapod_fwd = nullptr;
     int *tile_order = nullptr, *tile_order8 = nullptr, *heavy_cells = nullptr;
+    int *tile_order_rows = nullptr, *tile_order8_rows = nullptr;
     long long *grid_dbg = nullptr;       /* TRON_GRID_DEBUG: per-warp cycles of the last gridding launch */
     int nheavy = 0, heavy_r2 = -1;
     int *heavy_cells_big = nullptr; int nheavy_big = 0, heavy_r2_big = -1;
