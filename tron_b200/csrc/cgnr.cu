@@ -44,18 +44,22 @@ __device__ __forceinline__ double block_sum(double v)
     return t;                                            /* valid in thread 0 */
 }
 
-/* z [nb][nx][nx][nc]: clear row 0 and column 0, part[b][blockIdx.x] = partial |z_b|^2 */
+/* z [nb][nx][nx][nc]: clear row 0 and column 0, part[b][blockIdx.x] = partial |z_b|^2.
+ * One thread per pixel (one integer modulo per nc elements: with one per element these streaming kernels
+ * were bound by the division sequence, not by HBM). */
 __global__ void __launch_bounds__(CG_THREADS)
 cg_zz_kernel(float2 *__restrict__ z, double *__restrict__ part, int nx, int nc)
 {
-    const size_t N = (size_t)nx * nx * nc;
-    float2 *zb = z + (size_t)blockIdx.y * N;
+    const size_t npix = (size_t)nx * nx;
+    float2 *zb = z + (size_t)blockIdx.y * npix * nc;
     float acc = 0.f;
-    for (size_t i = (size_t)blockIdx.x * CG_THREADS + threadIdx.x; i < N; i += (size_t)gridDim.x * CG_THREADS) {
-        const size_t pix = i / nc;
-        if (pix < (size_t)nx || pix % nx == 0) { zb[i] = make_float2(0.f, 0.f); continue; }
-        const float2 q = zb[i];
-        acc += q.x * q.x + q.y * q.y;
+    for (size_t pix = (size_t)blockIdx.x * CG_THREADS + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * CG_THREADS) {
+        float2 *q = zb + pix * nc;
+        if (pix < (size_t)nx || pix % nx == 0) {
+            for (int c = 0; c < nc; ++c) q[c] = make_float2(0.f, 0.f);
+            continue;
+        }
+        for (int c = 0; c < nc; ++c) acc = fmaf(q[c].x, q[c].x, fmaf(q[c].y, q[c].y, acc));
     }
     const double t = block_sum((double)acc);
     if (threadIdx.x == 0) part[(size_t)blockIdx.y * CG_PARTS + blockIdx.x] = t;
@@ -69,16 +73,18 @@ __device__ __forceinline__ float cg_weight(int ro, int nro, float wa, float wb)
     return w;
 }
 
-/* v [nb][npe][nro][nc]: part[b][blockIdx.x] = partial <v_b, W' v_b> */
+/* v [nb][npe][nro][nc]: part[b][blockIdx.x] = partial <v_b, W' v_b>; npos = npe * nro sample positions */
 __global__ void __launch_bounds__(CG_THREADS)
-cg_vwv_kernel(const float2 *__restrict__ v, double *__restrict__ part, size_t n, int nro, int nc, float wa, float wb)
+cg_vwv_kernel(const float2 *__restrict__ v, double *__restrict__ part, size_t npos, int nro, int nc, float wa, float wb)
 {
-    const float2 *vb = v + (size_t)blockIdx.y * n;
+    const float2 *vb = v + (size_t)blockIdx.y * npos * nc;
     float acc = 0.f;
-    for (size_t i = (size_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * CG_THREADS) {
-        const int ro = (int)((i / nc) % nro);
-        const float2 q = vb[i];
-        acc = fmaf(cg_weight(ro, nro, wa, wb), q.x * q.x + q.y * q.y, acc);
+    for (size_t pos = (size_t)blockIdx.x * CG_THREADS + threadIdx.x; pos < npos; pos += (size_t)gridDim.x * CG_THREADS) {
+        const float w = cg_weight((int)(pos % nro), nro, wa, wb);
+        const float2 *q = vb + pos * nc;
+        float sq = 0.f;
+        for (int c = 0; c < nc; ++c) sq = fmaf(q[c].x, q[c].x, fmaf(q[c].y, q[c].y, sq));
+        acc = fmaf(w, sq, acc);
     }
     const double t = block_sum((double)acc);
     if (threadIdx.x == 0) part[(size_t)blockIdx.y * CG_PARTS + blockIdx.x] = t;
@@ -114,9 +120,8 @@ cg_step_kernel(float2 *__restrict__ x, const float2 *__restrict__ p, float2 *__r
     if (!update_r) return;
     float2 *rb = r + (size_t)b * n; const float2 *vb = v + (size_t)b * n;
     for (size_t i = (size_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * CG_THREADS) {
-        if ((i / nc) % nro == 0) continue;
-        float2 a = rb[i]; const float2 q = vb[i];
-        a.x = fmaf(-alpha, q.x, a.x); a.y = fmaf(-alpha, q.y, a.y);
+        float2 a = rb[i]; const float2 q = vb[i];          /* ro = 0 rows of r are zero and stay unused by the */
+        a.x = fmaf(-alpha, q.x, a.x); a.y = fmaf(-alpha, q.y, a.y);   /* gridding (W' = 0 there): no test needed */
         rb[i] = a;
     }
 }
@@ -147,18 +152,14 @@ cg_dir_kernel(float2 *__restrict__ p, const float2 *__restrict__ z, const double
     }
 }
 
-/* r_b = window of slice z0 + b (complex64 or complex-half), ro = 0 cleared */
+/* r_b = window of slice z0 + b (complex64 or complex-half) */
 __global__ void __launch_bounds__(CG_THREADS)
-cg_init_r_kernel(float2 *__restrict__ r, const void *__restrict__ in, size_t n, size_t window_stride, int nro, int nc,
-                 int half_in)
+cg_init_r_kernel(float2 *__restrict__ r, const void *__restrict__ in, size_t n, size_t window_stride, int half_in)
 {
     float2 *rb = r + (size_t)blockIdx.y * n;
     const size_t off = (size_t)blockIdx.y * window_stride;
-    for (size_t i = (size_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * CG_THREADS) {
-        float2 q = half_in ? __half22float2(((const __half2 *)in)[off + i]) : ((const float2 *)in)[off + i];
-        if ((i / nc) % nro == 0) q = make_float2(0.f, 0.f);
-        rb[i] = q;
-    }
+    for (size_t i = (size_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * CG_THREADS)
+        rb[i] = half_in ? __half22float2(((const __half2 *)in)[off + i]) : ((const float2 *)in)[off + i];
 }
 
 /* B: gridding + inverse FFT passes -> per-coil images in `coil`, forward deapodisation table */
@@ -203,7 +204,7 @@ int run_percoil_batch(tron_plan *p, const void *d_in, int z0, int nb, cudaStream
     if (niter > 1) {
         const size_t window_stride = (size_t)g.prof_slide * g.nro * nc;
         cg_init_r_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_r, (const char *)d_in + (size_t)z0 * window_stride * in_esz, n,
-                                                   window_stride, g.nro, nc, p->cfg.half_in);
+                                                   window_stride, p->cfg.half_in);
     }
     TRON_CUDA(cudaGetLastError());
     p->last_launches += 3;
@@ -227,7 +228,7 @@ int run_percoil_batch(tron_plan *p, const void *d_in, int z0, int nb, cudaStream
         }
         p->last_launches += 3;
         const int last = t == niter - 1;
-        cg_vwv_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_v, part_vwv, n, g.nro, nc, wa, wb);
+        cg_vwv_kernel<<<gr, CG_THREADS, 0, s>>>(p->cg_v, part_vwv, (size_t)g.npe1work * g.nro, g.nro, nc, wa, wb);
         cg_step_kernel<<<gr, CG_THREADS, 0, s>>>(x, p->cg_p, p->cg_r, p->cg_v, part_zz[t & 1], part_vwv, N, n,
                                                  g.nro, nc, sc, !last);
         TRON_CUDA(cudaGetLastError());
