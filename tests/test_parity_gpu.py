@@ -86,6 +86,9 @@ def test_pipeline_vs_oracle(lib, oracle, name):
     ([4, 1, 256, 48, 1], dict(adjoint=True, golden=True)),                                      # 256-point lines
     ([1, 1, 512, 64, 1], dict(adjoint=True)),                                                   # complex output
     ([2, 1, 512, 64, 1], dict(adjoint=True, gridos=1.0)),                                       # nothing cropped
+    ([2, 1, 256, 256, 1], dict(adjoint=False, undersamp=0.1)),                                  # forward, 512-point lines
+    ([1, 1, 128, 128, 1], dict(adjoint=False, golden=True, undersamp=0.2, skip_angles=3)),      # forward, 256-point lines
+    ([4, 1, 256, 256, 1], dict(adjoint=False, golden=True, undersamp=0.05, gridos=1.0)),        # forward, no padding
 ])
 @pytest.mark.parametrize("radix8", [False, True])
 def test_pipeline_line_lengths_of_the_benchmarks(lib, reflib, dims, flags, radix8, monkeypatch):
@@ -95,6 +98,8 @@ def test_pipeline_line_lengths_of_the_benchmarks(lib, reflib, dims, flags, radix
     torch_cuda()
     if radix8:
         monkeypatch.setenv("TRON_FFT_R8", "1")
+    else:
+        monkeypatch.setenv("TRON_FFT_P2W", "1")            # two-stage forward passes also for one or two planes
     h_in = synth_complex((int(np.prod(dims)),), stream=77)
     want = run_ref(reflib, dims, flags, h_in)
     with t.Plan(flags_to_cfg(dims, flags)) as p:

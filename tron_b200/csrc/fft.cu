@@ -990,6 +990,100 @@ p2w_adj_pass_b_coil(const float2 *__restrict__ tmp, void *__restrict__ outv, con
     }
 }
 
+/* forward passes on the two-stage line transform (the radix-8 versions above move every element through shared
+ * memory three times and sit at l1tex 74-83 %).  Both transform L lines per CTA and store all N outputs
+ * transposed through the staged buffer F[line][output], like p2w_adj_pass_a.
+ *   A: image rows (pad + deapodise on load, pad drops row 0 / column 0, tron.cu:449-450) -> tmp[plane][c][a]
+ *   B: tmp[plane][c][:] (zero padded to N) -> grid[plane][r][c] */
+template <int N, int R1>
+__device__ __forceinline__ void p2w_fwd_finish(float2 (&a)[P2W<N, R1>::M2][P2W<N, R1>::R2], float2 *smem, int l, int j,
+                                               const float2 *__restrict__ tw, float2 *__restrict__ out, int row_len,
+                                               int valid_lines)
+{
+    using G = P2W<N, R1>;
+    float2 *F = smem;
+    constexpr int PF = G::fpitch(N);
+    __syncthreads();                                  /* exchange buffer consumed: F may overwrite it */
+#pragma unroll
+    for (int m = 0; m < G::M2; ++m) {
+        const int b = j + m * G::T;
+        p2w_stage2<N, R1, -1>(a[m], b, tw);
+        const float sg = (b & 1) ? -1.f : 1.f;       /* input shift by N/2 = (-1)^k on the output */
+#pragma unroll
+        for (int t = 0; t < G::R2; ++t) {
+            const int c = (b + t * R1 + N / 2) & (N - 1);        /* output shift by N/2 */
+            F[l * PF + c] = make_float2(a[m][t].x * sg, a[m][t].y * sg);
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < N * G::L; idx += G::THREADS) {
+        const int c = idx / G::L, ll = idx % G::L;
+        if (ll < valid_lines) out[(size_t)c * row_len + ll] = F[ll * PF + c];
+    }
+}
+
+template <int N, int R1>
+__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 5)
+p2w_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const float *__restrict__ deapod,
+               const float2 *__restrict__ tw, int nx, int nch, int nc_total, int ch0, int half_in)
+{
+    extern __shared__ float2 smem[];
+    using G = P2W<N, R1>;
+    const int l = threadIdx.x / G::T, j = threadIdx.x % G::T;
+    float2 *xline = smem + l * G::LPX;
+    const int a0 = blockIdx.x * G::L, arow = a0 + l;
+    const int ch = blockIdx.y % nch;                  /* blockIdx.y = image * nch + channel */
+    const size_t img0 = (size_t)(blockIdx.y / nch) * nx * nx * nc_total;
+    const int w = (N - nx) / 2;
+    {
+        float2 v[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) {
+            const int b = j + q * G::T - w;           /* source column of padded column j + q*T */
+            v[q] = make_float2(0.f, 0.f);
+            if (arow >= 1 && arow < nx && b >= 1 && b < nx) {
+                const size_t e = img0 + ((size_t)arow * nx + b) * nc_total + ch0 + ch;
+                const float2 x = half_in ? __half22float2(((const __half2 *)imgv)[e]) : ((const float2 *)imgv)[e];
+                const float sc = __ldg(deapod + (size_t)arow * nx + b);
+                v[q] = make_float2(x.x * sc, x.y * sc);
+            }
+        }
+        p2w_stage1<N, R1, -1>(v, xline, j);
+    }
+    __syncwarp();
+    float2 a[G::M2][G::R2];
+#pragma unroll
+    for (int m = 0; m < G::M2; ++m) p2w_stage2_load<N, R1>(a[m], xline, j + m * G::T);
+    p2w_fwd_finish<N, R1>(a, smem, l, j, tw, tmp + (size_t)blockIdx.y * N * nx + a0, nx, nx - a0);
+}
+
+template <int N, int R1>
+__global__ void __launch_bounds__(P2W<N, R1>::THREADS, 5)
+p2w_fwd_pass_b(const float2 *__restrict__ tmp, float2 *__restrict__ grid, const float2 *__restrict__ tw, int nx)
+{
+    extern __shared__ float2 smem[];
+    using G = P2W<N, R1>;
+    const int l = threadIdx.x / G::T, j = threadIdx.x % G::T;
+    float2 *xline = smem + l * G::LPX;
+    const int c0 = blockIdx.x * G::L;
+    const int w = (N - nx) / 2;
+    const float2 *src = tmp + ((size_t)blockIdx.y * N + c0 + l) * nx;
+    {
+        float2 v[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) {
+            const int ai = j + q * G::T - w;
+            v[q] = (ai >= 0 && ai < nx) ? src[ai] : make_float2(0.f, 0.f);
+        }
+        p2w_stage1<N, R1, -1>(v, xline, j);
+    }
+    __syncwarp();
+    float2 a[G::M2][G::R2];
+#pragma unroll
+    for (int m = 0; m < G::M2; ++m) p2w_stage2_load<N, R1>(a[m], xline, j + m * G::T);
+    p2w_fwd_finish<N, R1>(a, smem, l, j, tw, grid + (size_t)blockIdx.y * N * N + c0, N, G::L);
+}
+
 template <int N, int R1> struct P2WLaunch {
     using G = P2W<N, R1>;
     static size_t smem_a(int nkeep) { return (size_t)std::max(G::L * G::LPX, G::L * G::fpitch(nkeep)) * sizeof(float2); }
@@ -999,6 +1093,20 @@ template <int N, int R1> struct P2WLaunch {
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_b_sos<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N / 2)));
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_pass_b_coil<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coil()));
         TRON_CUDA(cudaFuncSetAttribute(p2w_adj_fused<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
+        TRON_CUDA(cudaFuncSetAttribute(p2w_fwd_pass_a<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
+        TRON_CUDA(cudaFuncSetAttribute(p2w_fwd_pass_b<N, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a(N)));
+        return 0;
+    }
+    static int fwd(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)
+    {
+        const int nimg = a.nimg > 0 ? a.nimg : 1;
+        dim3 ga((f.nkeep + G::L - 1) / G::L, a.nch * nimg);
+        p2w_fwd_pass_a<N, R1><<<ga, G::THREADS, smem_a(N), s>>>(a.img, a.tmp, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total,
+                                                                a.ch0, a.half_in);
+        TRON_CUDA(cudaGetLastError());
+        dim3 gb(N / G::L, a.nch * nimg);
+        p2w_fwd_pass_b<N, R1><<<gb, G::THREADS, smem_a(N), s>>>(a.tmp, a.grid, f.tw, f.nkeep);
+        TRON_CUDA(cudaGetLastError());
         return 0;
     }
     /* both passes in one launch (modes 0 / 3, nkeep = N/2); a.sync holds 2 * nslices zeroed counters */
@@ -1086,6 +1194,13 @@ template <int N, int L> struct P2Launch {
     }
     static int fwd(const FftPlan &f, const FwdFftLaunch &a, cudaStream_t s)
     {
+        if constexpr (P2WSplit<N>::R1 != 0) {
+            /* a single plane gives the 128-thread CTAs of the two-stage passes too few blocks to fill the GPU
+             * (256^2 forward transform: 40 vs 33 us); from a few planes on they win (CGNR: 149 -> 144 us per slice) */
+            const bool force = getenv("TRON_FFT_P2W") != nullptr;
+            if (getenv("TRON_FFT_R8") == nullptr && (force || a.nch * (a.nimg > 0 ? a.nimg : 1) >= 4))
+                return P2WLaunch<N, P2WSplit<N>::R1>::fwd(f, a, s);
+        }
         const int nimg = a.nimg > 0 ? a.nimg : 1;
         dim3 ga((f.nkeep + L - 1) / L, a.nch * nimg);
         p2_fwd_pass_a<N, L><<<ga, THREADS, SMEM, s>>>(a.img, a.tmp, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total, a.ch0, a.half_in);
