@@ -437,7 +437,9 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     }
     for (int z0 = 0, nb = 0; z0 < p->nslices; z0 += nb, i ^= 1) {
         nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
-        const int hb = host ? (p->batch < HOST_BATCH_MAX ? p->batch : (HOST_BATCH_MAX / gs) * gs) : p->batch;
+        static const int hbm_env = getenv("TRON_HOST_BATCH") ? atoi(getenv("TRON_HOST_BATCH")) : 0;
+        const int hbm = hbm_env >= gs ? hbm_env : HOST_BATCH_MAX;
+        const int hb = host ? (p->batch < hbm ? p->batch : (hbm / gs) * gs) : p->batch;
         if (host && nb > hb) nb = hb;
         if (host && hb >= 8 * gs) {
             /* host mode ramps the batch size up at the start and down at the end, so that the first
