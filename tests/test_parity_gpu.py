@@ -243,6 +243,62 @@ def test_grid_index_map_bit_exact_wide(lib, reflib_wide):
         assert np.array_equal(mine != 0, want != 0), "index map differs for samples %s" % ids
 
 
+@pytest.mark.parametrize("nchan,half,flags,env", [
+    (6, False, dict(golden=True, undersamp=0.25, prof_slide=3), {}),                             # 4-slice groups, chains of 8 groups: sliding-window differences
+    (6, False, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_TILE_DELTA": "0"}),       # every group gridded in full
+    (4, False, dict(golden=True, undersamp=0.25, prof_slide=2, skip_angles=5), {"TRON_TILE_GPER": "3"}),   # chains of 3 groups
+    (6, False, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_TILE_CAP": "1024", "TRON_TILE_DELTA": "0"}),      # many rounds per group
+    (6, False, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_TILE_CAP": "512"}),
+    (6, False, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_TILE_GPER": "3", "TRON_TILE_NEAR": "0", "TRON_TILE_DELTA": "0"}),
+    (6, False, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_TILE_GPER": "1", "TRON_TILE_NEAR": "1000"}),
+    (2, False, dict(golden=True, undersamp=0.5, prof_slide=2, skip_angles=11), {"TRON_TILE_CAP": "512"}),
+    (4, False, dict(golden=False, prof_slide=40, undersamp=0.4), {}),                            # linear angles: one shared table, gs = 1
+    (8, False, dict(golden=True), {}),                                                           # one slice
+    (6, True, dict(golden=True, undersamp=0.25, prof_slide=3), {}),                              # fp16 storage: 24-byte samples
+    (2, True, dict(golden=True, undersamp=0.3, prof_slide=5), {"TRON_TILE_CAP": "256"}),
+])
+def test_tile_kernel_matches_l1_gather(lib, monkeypatch, nchan, half, flags, env):
+    """grid_tile.cu (spoke runs staged in shared memory by cp.async.bulk, one copy pipeline per warp) visits the
+    same taps as grid.cu (taps through L1) with the same weights; only cells whose spoke window wraps around the
+    end of the sorted table are summed in another order (rounds go through the table front to back) -- and, when the
+    sliding-window difference tables are in use, all cells of the slice groups that are built from their predecessor."""
+    import tron_b200 as t
+    torch = torch_cuda()
+    nro, npe1 = 128, 150
+    s = synth_complex((npe1, nro, nchan), stream=90 + nchan)
+    raw = s.view(np.float32).astype(np.float16) if half else s.view(np.float32)
+    outs = []
+    for tile in (False, True):
+        for k in ("TRON_NO_TILE", "TRON_TILE_CAP", "TRON_TILE_GPER", "TRON_TILE_NEAR", "TRON_TILE_DELTA"):
+            monkeypatch.delenv(k, raising=False)
+        if tile:
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+        else:
+            monkeypatch.setenv("TRON_NO_TILE", "1")
+        with t.Plan(t.make_config([nchan, 1, nro, npe1, 1], adjoint=True, half_in=half, **flags)) as p:
+            ns, n = p.geom.nz, p.geom.nxos
+            d_s = torch.from_numpy(raw.copy()).cuda()
+            d_g = torch.full((ns, nchan, n, n, 2), 7.0, dtype=torch.float32, device="cuda")
+            p.grid_device(d_g.data_ptr(), d_s.data_ptr(), 0, ns, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            outs.append(d_g.cpu().numpy())
+    assert np.abs(outs[0]).max() > 0
+    if env.get("TRON_TILE_DELTA") == "0" or flags.get("prof_slide", 0) in (0, 40):
+        assert np.array_equal(outs[0] != 0, outs[1] != 0)
+        assert rel_l2(outs[1], outs[0]) <= 1e-7
+        assert np.mean(outs[0] != outs[1]) < 0.02
+    else:
+        # sliding-window differences: slice z+1 = slice z - leaving + entering spokes, re-anchored every chain;
+        # same taps and weights, another order of additions.  A cell all of whose taps have left the window
+        # again keeps their rounding residue instead of an exact zero (this sparse test geometry has such
+        # cells; with the benchmark shapes every cell inside the last annulus always holds taps).
+        assert rel_l2(outs[1], outs[0]) <= 5e-7
+        empty = outs[0] == 0
+        assert np.abs(outs[1][empty]).max() <= 1e-6 * np.abs(outs[0]).max()
+        assert np.array_equal(outs[0][:1] != 0, outs[1][:1] != 0)          # the chain's first group is gridded in full
+
+
 def _degrid_mine(t, torch, grid, n_img, nchan, **flags):
     """grid: (n, n, nchan) complex64 in the reference's interleaved order -> (npe, nro, nchan)."""
     cfg = t.make_config([nchan, 1, n_img, n_img, 1], adjoint=False, **flags)

@@ -133,9 +133,10 @@ extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
 static void plan_release(tron_plan *p)
 {
     if (!p) return;
+    cudaFree(p->tabs_d.gx); cudaFree(p->tabs_d.lut);
     cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.gx); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
     fft_plan_free(p->fft);
-    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->tile_order_rows); cudaFree(p->tile_order8_rows); cudaFree(p->heavy_cells); cudaFree(p->heavy_cells_big); cudaFree(p->grid_dbg);
+    cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->tile_order_rows); cudaFree(p->tile_order8_rows); cudaFree(p->heavy_cells); cudaFree(p->heavy_cells_big); cudaFree(p->grid_dbg); cudaFree(p->tile_win8); cudaFree(p->tile_sched8);
     cudaFree(p->d_grid); cudaFree(p->d_tmp); cudaFree(p->d_gridi); cudaFree(p->d_in); cudaFree(p->d_out);
     cudaFree(p->fft_sync);
     cudaFree(p->d_coil); cudaFree(p->cg_r); cudaFree(p->cg_v); cudaFree(p->cg_z); cudaFree(p->cg_p); cudaFree(p->cg_part);
@@ -262,14 +263,40 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
          * warp-per-cell path than long ones (grid.cu: build_heavy_cells, launch_grid_cg picks per launch) */
         PLAN_TRY(build_heavy_cells(&p->heavy_cells, &p->nheavy, &p->heavy_r2, n, p->tabs.npe, cfg->kernwidth, 24));
         PLAN_TRY(build_heavy_cells(&p->heavy_cells_big, &p->nheavy_big, &p->heavy_r2_big, n, p->tabs.npe, cfg->kernwidth, 96));
+        /* enough cell-groups per launch to hide the long cells: only the innermost ones take the warp path.
+         * Decided once per plan (from the launch length the device pipeline uses), never per launch. */
+        {
+            const int gsz = p->tabs.gs > 0 ? p->tabs.gs : 1;
+            const int per_launch = p->nslices < 256 ? p->nslices : 256;
+            p->heavy_big = (double)n * n * ((per_launch + gsz - 1) / gsz) >= 2.0e6;
+            if (getenv("TRON_HEAVY_BIG")) p->heavy_big = atoi(getenv("TRON_HEAVY_BIG")) != 0;
+        }
+        PLAN_TRY(build_tile_windows(&p->tile_win8, p->tabs.cells, n, p->tabs.nbins, p->stream));
+        /* sliding windows: all but the first slice group of a chain are gridded from what enters and leaves
+         * the window (grid_tile.cu); worth it when that is clearly fewer spokes than a group's union window */
+        {
+            const int gsz = p->tabs.gs, ne = 2 * gsz * g.prof_slide;
+            const bool plain = p->kb.fast && g.nro == g.nxos && p->nch == g.nc && (g.nc == 2 || g.nc == 4 || g.nc == 6 || g.nc == 8);
+            const char *ed = getenv("TRON_TILE_DELTA");
+            if (cfg->golden_angle && gsz == 4 && plain && p->nslices > gsz && 5 * ne <= 4 * p->tabs.npe
+                && !getenv("TRON_NO_TILE") && !(ed && atoi(ed) == 0)) {
+                p->chain = getenv("TRON_TILE_GPER") && atoi(getenv("TRON_TILE_GPER")) > 0 ? atoi(getenv("TRON_TILE_GPER")) : 8;
+                const int skip = cfg->skip_angles + g.slice_begin * g.prof_slide;
+                PLAN_TRY(build_delta_tables(p->tabs_d, p->tabs, p->tabs.ntab, gsz * g.prof_slide, skip, g.npe1work,
+                                            g.prof_slide, gsz, p->nslices, p->stream));
+            }
+        }
+        PLAN_TRY(build_tile_schedule(&p->tile_sched8, &p->n_near8, n, 8,
+                                     getenv("TRON_TILE_NEAR") ? (float)atof(getenv("TRON_TILE_NEAR")) : 32.f));
     }
     PLAN_CUDA(cudaMalloc(&p->deapod_adj, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_CUDA(cudaMalloc(&p->deapod_fwd, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_TRY(launch_deapod_tables(p->deapod_adj, p->deapod_fwd, g.nx, n, cfg->kernwidth, cfg->gridos, p->stream));
 
     p->batch = cfg->adjoint ? pick_batch(p) : 1;
-    if (cfg->adjoint && p->tabs.gs > 1) {                /* launches start on group boundaries */
-        p->batch = ((p->batch + p->tabs.gs - 1) / p->tabs.gs) * p->tabs.gs;
+    if (cfg->adjoint && p->tabs.gs > 1) {                /* launches start on group (chain) boundaries */
+        const int q = p->tabs.gs * (p->chain > 0 ? p->chain : 1);
+        p->batch = ((p->batch + q - 1) / q) * q;
     }
     p->stage_timing = getenv("TRON_STAGE_TIMING") != nullptr;
     if (cfg->adjoint && getenv("TRON_GRID_DEBUG")) {
@@ -335,7 +362,10 @@ GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d
     L.tab_cs = p->tabs.cs; L.tab_pe = p->tabs.pe; L.tab_gx = p->tabs.gx; L.lut = p->tabs.lut; L.cells = p->tabs.cells;
     L.tile_order = p->tile_order; L.tile_order8 = p->tile_order8;
     L.tile_order_rows = p->tile_order_rows; L.tile_order8_rows = p->tile_order8_rows;
-    L.heavy_cells = p->heavy_cells; L.nheavy = p->nheavy; L.heavy_r2 = p->heavy_r2;
+    if (p->heavy_big) { L.heavy_cells = p->heavy_cells_big; L.nheavy = p->nheavy_big; L.heavy_r2 = p->heavy_r2_big; }
+    else { L.heavy_cells = p->heavy_cells; L.nheavy = p->nheavy; L.heavy_r2 = p->heavy_r2; }
+    L.tile_win8 = p->tile_win8; L.tile_sched8 = p->tile_sched8; L.n_near8 = p->n_near8;
+    L.tab_gx_d = p->tabs_d.gx; L.lut_d = p->tabs_d.lut; L.npe_d = p->tabs_d.npe; L.chain = p->chain;
     L.heavy_cells_big = p->heavy_cells_big; L.nheavy_big = p->nheavy_big; L.heavy_r2_big = p->heavy_r2_big;
     L.tab_per_slice = p->tabs.ntab > 1 ? 1 : 0;
     L.nbins = p->tabs.nbins;
@@ -426,7 +456,7 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     const size_t grid_elems = (size_t)p->batch * p->nch * g.nxos * g.nxos;
     size_t spokes_up = 0;
     int i = 0;
-    const int gs = p->tabs.gs > 0 ? p->tabs.gs : 1;
+    const int gs = (p->tabs.gs > 0 ? p->tabs.gs : 1) * (p->chain > 0 ? p->chain : 1);   /* launch granularity */
     /* TRON_HOST_TRACE: when did the last upload, the last kernel and the last download finish? */
     static const bool trace = getenv("TRON_HOST_TRACE") != nullptr;
     cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -441,7 +471,7 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
         const int hbm = hbm_env >= gs ? hbm_env : HOST_BATCH_MAX;
         const int hb = host ? (p->batch < hbm ? p->batch : (hbm / gs) * gs) : p->batch;
         if (host && nb > hb) nb = hb;
-        if (host && hb >= 8 * gs) {
+        if (host && hb >= 2 * gs) {
             /* host mode ramps the batch size up at the start and down at the end, so that the first
              * upload and the last download (which nothing overlaps) are short */
             int ramp = hb;

@@ -50,6 +50,12 @@ struct GridLaunch {               /* everything the gridding kernel needs */
     float sdc_as, sdc_bs;         /* sdc_a * scale, sdc_b * scale: the gather folds the output scale into the weight */
     int half_in;
     long long *dbg;               /* optional per-warp cycle counts [blocks][8] */
+    const float4 *tab_gx_d = nullptr;  /* grid_tile.cu: sliding-window difference tables (same layout as tab_gx), or null */
+    const int *lut_d = nullptr; int npe_d = 0;
+    int chain = 0;                     /* groups per chain when difference tables are in use (fixed by the plan) */
+    const int2 *tile_win8 = nullptr;   /* grid_tile.cu: per 8x4 warp footprint, packed angular-bin window (union of its cells) */
+    const int *tile_sched8 = nullptr;  /* grid_tile.cu: tile schedule, the n_near8 tiles next to DC first */
+    int n_near8 = 0;
     int zero_r2;                  /* cells with X^2 + Y^2 > zero_r2 can hold no sample and are NOT stored (the FFT pass
                                      that follows does not fetch them); INT_MAX: every cell is stored */
 };
@@ -66,6 +72,12 @@ struct DegridLaunch {
 };
 
 int launch_grid(const GridLaunch &g, cudaStream_t s);
+bool grid_tile_applicable(const GridLaunch &g);
+int launch_grid_tile(const GridLaunch &g, cudaStream_t s);
+int build_tile_windows(int2 **d_win, const int2 *cells, int n, int nbins, cudaStream_t s);
+int build_tile_schedule(int **d_order, int *n_near, int n, int th, float near_r);
+int build_delta_tables(SpokeTables &d, const SpokeTables &full, int ntab, int tab_stride, int skip, int win,
+                       int slide, int gs, int nslices, cudaStream_t s);
 bool grid_wide_applicable(const GridLaunch &g);
 int launch_grid_wide(const GridLaunch &g, cudaStream_t s);
 int launch_degrid(const DegridLaunch &d, cudaStream_t s);
@@ -157,6 +169,10 @@ struct tron_plan {
     long long *grid_dbg = nullptr;       /* TRON_GRID_DEBUG: per-warp cycles of the last gridding launch */
     int nheavy = 0, heavy_r2 = -1;
     int *heavy_cells_big = nullptr; int nheavy_big = 0, heavy_r2_big = -1;
+    int heavy_big = 0;                   /* which of the two lists this plan's launches use (fixed per plan: one summation order) */
+    int2 *tile_win8 = nullptr; int *tile_sched8 = nullptr; int n_near8 = 0;   /* grid_tile.cu */
+    tronb::SpokeTables tabs_d;           /* grid_tile.cu: sliding-window difference tables (empty: not in use) */
+    int chain = 0;                       /* slice groups per chain: the first is gridded in full, the others from differences */
     int zero_r2 = 0x7fffffff;            /* adjoint: cells beyond this squared radius never receive a sample */
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
     int *fft_sync = nullptr; int fft_ring = 0;      /* single-launch FFT stage: counters, slices of d_tmp used as a ring */
