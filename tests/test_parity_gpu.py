@@ -362,7 +362,14 @@ def test_slice_shards_concatenate(lib):
             part = p.recon_host(h_in[int(g.shard_in_offset):int(g.shard_in_offset + g.shard_in_elems)])
             assert part.size == int(g.shard_out_elems)
             parts.append(part)
-    assert np.array_equal(np.concatenate(parts), full)
+    # A slice's taps and weights do not depend on the shard; the ORDER of its additions does (slice groups and
+    # their sorted spoke tables start at the shard's first slice), so shards agree to rounding, not bit for bit.
+    cat = np.concatenate(parts)
+    assert rel_l2(cat, full) <= 1e-6
+    per_slice = [rel_l2(a, b) for a, b in zip(cat.reshape(nz, -1), full.reshape(nz, -1))]
+    assert max(per_slice) <= 1e-6
+    with t.Plan(flags_to_cfg(dims, flags, batch_slices=7)) as p:       # same plan shape again: bit-identical
+        assert np.array_equal(p.recon_host(h_in), full)
 
 
 def test_coil_shards_sum_of_squares(lib):
