@@ -11,14 +11,26 @@ pointer).  One "step" = the whole 956-slice job.
   value  : coil-samples/s with the acquisition already resident in HBM
            (tron_recon_device, CUDA events on the launching stream)
   e2e    : the same job through the host-buffer C-ABI call (tron_recon_host):
-           pinned host input -> H2D -> kernels -> D2H, wall clock
+           pinned host input -> H2D -> kernels -> D2H, wall clock; with the rel-L2
+           distance of its output from the device path's and the cost of the two
+           copies alone (copy_floor_ms) -- the step cannot beat its PCIe traffic
   roofline: the gridding kernel alone (tron_grid_device), algorithmic bytes
            8*nc*(nro*npe1work + nxos^2) per slice over CUDA-event time
+  parity : slices of this run's output against the unmodified reference run on
+           the same input windows (oracle/_ref as checker, untimed)
+  e2e_cold: the reference's own span (tron.cu:726-786: init + buffers + recon +
+           shutdown) through the legacy recon_radial2d symbol
+  other_configs (N = 1): cfg1, cfg3 shard, cfg4 shard, cfg5 pair -- value, e2e,
+           roofline and the reference's time for the same job (<= 6-coil chunks,
+           sampled and scaled)
+  strong / coil_sharded (N > 1): ONE cfg2 acquisition sharded by slice; the cfg5
+           pair with 64/N coils per GPU and the library's single ncclReduce
   cpu_baseline: OpenMP C gridding operator (oracle/, "port") on the host cores,
            bounded sample of the same slices
   --impl reference: the UNMODIFIED reference (oracle/_ref, tron.cu compiled in
            place for sm_100 + cuFFT) through its own recon_radial2d on pinned
            host buffers on the same GPU; rank 0 only.
+  --lean : the headline line only (kernel experiments).
 
 Multi-GPU (torchrun, one rank per GPU): every rank reconstructs its own
 acquisition of the same shape (slices/frames are independent, no data-path
@@ -130,6 +142,19 @@ def bind_to_gpu_numa(local):
     return None
 
 
+class _StdoutToStderr:
+    """NCCL announces its version on stdout at the first communicator; stdout carries the JSON line only."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def dist_setup(n_gpus):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -140,6 +165,9 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with _StdoutToStderr():                      # NCCL's version banner belongs on stderr
+            dist.barrier()
+            torch.cuda.synchronize()
     else:
         torch.cuda.set_device(0)
     return rank, world, local
@@ -197,6 +225,375 @@ def cpu_baseline(dims, flags, geom, budget_s=15.0):
                       % (nsl, geom["nz"], dt)}
 
 
+def rel_l2_t(a, b):
+    """relative L2 distance of two torch tensors (float64 accumulation)."""
+    d = (a.double() - b.double()).norm().item()
+    return d / max(b.double().norm().item(), 1e-300)
+
+
+def parity_vs_reference(torch, d_out, d_in, dims, flags, g, slices):
+    """Checker, outside every timed region: slices of THIS run's output against the unmodified reference
+    (oracle/_ref) run on the same windows of the same input.  Slice z of a sliding-window job is the
+    reference's single-slice job on spokes [z*slide, z*slide + npe1work) with skip_angles = z*slide
+    (absolute golden-angle index, tron.cu:630,738)."""
+    try:
+        from oracle.oracle import RefLib
+        ref = RefLib()
+    except Exception as e:
+        return {"unavailable": "oracle/_ref not built: %s" % e}
+    nc, nro, win, slide = g["nc"], g["nro"], g["npe1work"], g["prof_slide"]
+    if nc > ref.maxchan:
+        return {"unavailable": "nc = %d > MAXCHAN of the stock reference" % nc}
+    npix = g["nx"] * g["ny"]
+    worst, per = 0.0, {}
+    for z in slices:
+        w = d_in[2 * nc * nro * slide * z: 2 * nc * nro * (slide * z + win)].cpu().numpy().view(np.complex64)
+        ref.configure([nc, 1, nro, win, 1], True, golden=flags.get("golden", False), gridos=flags.get("gridos", 2.0),
+                      kernwidth=flags.get("kernwidth", 2.0), undersamp=float(win + 0.5) / nro, prof_slide=0,
+                      skip_angles=flags.get("skip_angles", 0) + z * slide)
+        assert ref.geom["npe1work"] == win and ref.geom["nz"] == 1
+        want = torch.from_numpy(ref.recon(w).view(np.float32))
+        got = d_out[2 * npix * z: 2 * npix * (z + 1)].cpu()
+        per[str(z)] = rel_l2_t(got, want)
+        worst = max(worst, per[str(z)])
+    return {"rel_l2": worst, "tolerance": 1e-5, "ok": bool(worst <= 1e-5), "slices": per,
+            "against": "oracle/_ref (unmodified tron.cu + cuFFT on this GPU), same input windows"}
+
+
+def copy_floor_ms(torch, h_in, d_in, h_out, d_out, reps, world):
+    """What the two PCIe copies of the end-to-end step cost on their own: the step's H2D and D2H bytes from the
+    same pinned buffers, concurrently on two streams, wall clock, max over ranks."""
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    def once():
+        with torch.cuda.stream(s_in):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_out, non_blocking=True)
+    once()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    return max_over_ranks((time.perf_counter() - t0) / reps, world) * 1e3
+
+
+def grid_roofline(torch, plan, g, d_in, half_in, B, kernel_name, workload):
+    """The gridding kernel alone (tron_grid_device), CUDA events on the launching stream, against the HBM peak."""
+    n, nc = g["nxos"], g["nc"]
+    stream = torch.cuda.current_stream().cuda_stream
+    d_grid = torch.empty(B * nc * n * n * 2, dtype=torch.float32, device="cuda")
+    starts = list(range(0, g["nz"] - B + 1, B)) or [0]
+    for z0 in starts[:4]:
+        plan.grid_device(d_grid.data_ptr(), d_in.data_ptr(), z0, B, stream)
+    torch.cuda.synchronize()
+    reps = max(1, 8 // len(starts))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for z0 in starts:
+            plan.grid_device(d_grid.data_ptr(), d_in.data_ptr(), z0, B, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    grid_ms = e0.elapsed_time(e1) / (reps * len(starts))
+    del d_grid
+    bytes_per_slice = (4 if half_in else 8) * nc * g["nro"] * g["npe1work"] + 8 * nc * n * n
+    achieved = bytes_per_slice * B / (grid_ms * 1e-3) / 1e9
+    peak, peak_src = peak_hbm()
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "grid_traffic.json")
+    if os.path.isfile(tj):
+        try:
+            j = json.load(open(tj))
+            per_slice = j.get(workload + "_bytes_per_slice")
+            traffic = per_slice * B if per_slice else None
+            traffic_src = j.get(workload + "_source") if per_slice else None
+        except Exception:
+            traffic = None
+    return {"bound": "hbm", "kernel": "%s (tron_grid_device, %d slices/launch)" % (kernel_name, B),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bytes_per_slice * B, "ms_per_launch": grid_ms}, grid_ms
+
+
+def time_device(torch, fn, steps, warmup, world=1):
+    for _ in range(warmup):
+        fn()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world) / steps
+
+
+def time_wall(torch, fn, steps, warmup, world=1):
+    for _ in range(warmup):
+        fn()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    dt = max_over_ranks((time.perf_counter() - t0) / steps, world)
+    barrier(world)
+    return dt * 1e3
+
+
+def reference_chunks_ms(dims, flags, slices_timed, slices_total, adjoint=True):
+    """the stock reference holds at most MAXCHAN = 6 channels (tron.h:51), so a many-coil job is
+    timed in <= 6-coil chunks (its recon_radial2d span on pinned host buffers, per-call init included) on
+    `slices_timed` slices and scaled to `slices_total`.  Returns (ms, description) or (None, why)."""
+    try:
+        from oracle.oracle import RefLib
+        ref = RefLib()
+    except Exception as e:
+        return None, "oracle/_ref not built: %s" % e
+    nc = dims[0]
+    rng = np.random.Generator(np.random.Philox(key=20261017 + 77))
+    total, chunks = 0.0, []
+    c0 = 0
+    while c0 < nc:
+        c = min(ref.maxchan if adjoint else nc, nc - c0)      # degridradial2d has no channel limit (tron.cu:540-577)
+        d = [c] + list(dims[1:])
+        h = rng.standard_normal(int(np.prod(d)) * 2, dtype=np.float32).view(np.complex64)
+        ref.configure(d, adjoint, golden=flags.get("golden", False), gridos=flags.get("gridos", 2.0),
+                      kernwidth=flags.get("kernwidth", 2.0), undersamp=flags.get("undersamp", 1.0),
+                      prof_slide=flags.get("prof_slide", 0))
+        ref.recon(h, return_seconds=True)                      # warm-up (cuFFT plan caches, clocks)
+        _, sec = ref.recon(h, return_seconds=True)
+        total += sec
+        chunks.append(c)
+        c0 += c
+    scale = slices_total / float(slices_timed)
+    return total * 1e3 * scale, "oracle/_ref in coil chunks %s on %d of %d slices, scaled x%.1f" % (
+        chunks, slices_timed, slices_total, scale)
+
+
+def measure_adjoint_config(torch, t, name, local, steps=3, warmup=2, with_reference=True, ref_slices=2):
+    """One of the other BASELINE shapes on this GPU: device-resident value, host-buffer e2e, gridding roofline and
+    the reference's time for the same job (chunked, sampled)."""
+    dims, flags, desc = WORKLOADS[name]
+    plan = t.Plan(t.make_config(dims, device=local, **flags))
+    g = plan.geom.as_dict()
+    nsamp = g["nc"] * g["nro"] * g["npe1work"] * g["nz"]
+    in_elems, out_elems = g["shard_in_elems"], g["shard_out_elems"]
+    d_in, h_in = make_input(torch, in_elems, 7)
+    d_out = torch.zeros(out_elems * 2, dtype=torch.float32, device="cuda")
+    h_out = torch.zeros(out_elems * 2, dtype=torch.float32, pin_memory=True)
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = time_device(torch, lambda: plan.recon_device(d_out.data_ptr(), d_in.data_ptr(), stream), steps, warmup)
+    launches = plan.last_launches()
+    e2e_ms = time_wall(torch, lambda: plan.recon_host_ptr(h_out.data_ptr(), h_in.data_ptr()), steps, 1)
+    B = min(256, g["nz"])
+    kern = "grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel"
+    roof, grid_ms = grid_roofline(torch, plan, g, d_in, False, B, kern, name)
+    roof["share_of_step"] = grid_ms * (g["nz"] / B) / ms
+    out = {"workload": desc, "value": nsamp / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+           "images_per_s": g["nz"] / (ms * 1e-3), "gpu_launches_per_step": launches,
+           "e2e": {"value": nsamp / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": in_elems * 8, "d2h_bytes_per_step": out_elems * 8,
+                   "rel_l2_vs_device": rel_l2_t(h_out, d_out.cpu())},
+           "roofline": roof}
+    plan.close()
+    del d_in, d_out, h_in, h_out
+    torch.cuda.empty_cache()
+    if with_reference:
+        k = min(ref_slices, g["nz"])
+        rd = list(dims)
+        rd[3] = g["npe1work"] + g["prof_slide"] * (k - 1)
+        ref_ms, how = reference_chunks_ms(rd, flags, k, g["nz"])
+        out["reference_ms"] = ref_ms
+        out["reference_how"] = how
+        if ref_ms:
+            out["speedup_vs_reference_e2e"] = ref_ms / e2e_ms
+    return out
+
+
+def measure_cfg1(torch, t, local, steps=20, warmup=5):
+    """BASELINE cfg1: Shepp-Logan 256^2 forward (RUNME1 flags = defaults) then adjoint of the result, one GPU.
+    One slice: launch-latency bound (the HBM time of the pair is ~1.3 us)."""
+    from util import shepp_logan
+    ph = np.ascontiguousarray(shepp_logan(256).ravel())
+    fw = t.Plan(t.make_config([1, 1, 256, 256, 1], adjoint=False, device=local))
+    gf = fw.geom.as_dict()
+    ad = t.Plan(t.make_config([1, 1, gf["nro"], gf["npe1work"], 1], adjoint=True, device=local))
+    ga = ad.geom.as_dict()
+    d_img = torch.from_numpy(ph.view(np.float32).copy()).cuda()
+    d_smp = torch.zeros(gf["out_elems"] * 2, dtype=torch.float32, device="cuda")
+    d_rec = torch.zeros(ga["out_elems"] * 2, dtype=torch.float32, device="cuda")
+    h_img = torch.from_numpy(ph.view(np.float32).copy()).pin_memory()
+    h_smp = torch.zeros(gf["out_elems"] * 2, dtype=torch.float32, pin_memory=True)
+    h_rec = torch.zeros(ga["out_elems"] * 2, dtype=torch.float32, pin_memory=True)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def pair():
+        fw.recon_device(d_smp.data_ptr(), d_img.data_ptr(), stream)
+        ad.recon_device(d_rec.data_ptr(), d_smp.data_ptr(), stream)
+
+    def pair_host():
+        fw.recon_host_ptr(h_smp.data_ptr(), h_img.data_ptr())
+        ad.recon_host_ptr(h_rec.data_ptr(), h_smp.data_ptr())
+
+    ms = time_device(torch, pair, steps, warmup)
+    ms_fw = time_device(torch, lambda: fw.recon_device(d_smp.data_ptr(), d_img.data_ptr(), stream), steps, 2)
+    e2e_ms = time_wall(torch, pair_host, steps, 2)
+    nsamp = 2 * gf["nro"] * gf["npe1work"]
+    peak, peak_src = peak_hbm()
+    n = gf["nxos"]
+    b_interp = 8 * (gf["nro"] * gf["npe1work"] + n * n)            # SURVEY 8d, one channel, either direction
+    out = {"workload": "BASELINE cfg1: Shepp-Logan 256^2 forward (defaults, linear angles) + adjoint of the result, 1 coil",
+           "value": nsamp / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "forward_ms": ms_fw,
+           "adjoint_ms": ms - ms_fw, "gpu_launches_per_step": fw.last_launches() + ad.last_launches(),
+           "e2e": {"value": nsamp / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(ph.nbytes + gf["out_elems"] * 8),
+                   "d2h_bytes_per_step": int(gf["out_elems"] * 8 + ga["out_elems"] * 8)},
+           "roofline": {"bound": "hbm", "kernel": "forward + adjoint pair, all six launches (one slice: latency bound)",
+                        "achieved": (2 * b_interp + 4 * 8 * n * n) / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": (2 * b_interp + 4 * 8 * n * n) / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": 2 * b_interp + 4 * 8 * n * n}}
+    try:
+        from oracle.oracle import RefLib
+        ref = RefLib()
+        ref.configure([1, 1, 256, 256, 1], False)
+        ref.recon(ph)
+        want_s, s1 = ref.recon(ph, return_seconds=True)
+        ref.configure([1, 1, 512, 512, 1], True)
+        ref.recon(want_s)
+        want_i, s2 = ref.recon(want_s, return_seconds=True)
+        out["reference_ms"] = (s1 + s2) * 1e3
+        out["reference_how"] = "oracle/_ref, recon_radial2d span of each direction on pinned host buffers"
+        out["speedup_vs_reference_e2e"] = out["reference_ms"] / e2e_ms
+        out["parity"] = {"forward_rel_l2": rel_l2_t(h_smp, torch.from_numpy(want_s.view(np.float32))),
+                         "pair_rel_l2": rel_l2_t(h_rec, torch.from_numpy(want_i.view(np.float32)))}
+    except Exception as e:
+        out["reference_ms"] = None
+        out["reference_how"] = "unavailable: %s" % e
+    fw.close(); ad.close()
+    return out
+
+
+class Cfg5Pair:
+    """BASELINE cfg5: fp16-storage forward + adjoint pair, 1024 matrix, 2x grid, kernel width 6, 64 coils split
+    over `world` ranks; the adjoint ends in a partial sum of squares per rank and ONE ncclReduce (library call,
+    tron_coil_reduce) + sqrt on rank 0."""
+
+    def __init__(self, torch, t, rank, world, local, comm):
+        self.torch, self.t, self.rank, self.world, self.comm = torch, t, rank, world, comm
+        nc, nx = 64, 1024
+        self.nc, self.ncl = nc, nc // world
+        ncl = self.ncl
+        self.fw = t.Plan(t.make_config([ncl, 1, nx, nx, 1], adjoint=False, kernwidth=6.0, half_in=True, half_out=True, device=local))
+        self.gf = gf = self.fw.geom.as_dict()
+        self.ad = t.Plan(t.make_config([ncl, 1, gf["nro"], gf["npe1work"], 1], adjoint=True, kernwidth=6.0, half_in=True,
+                                       sos_partial=True, device=local))
+        self.ga = ga = self.ad.geom.as_dict()
+        gen = torch.Generator(device="cuda"); gen.manual_seed(20261017 + 5 + 1000 * rank)
+        self.npix = ga["nx"] * ga["ny"]
+        self.d_img = torch.randn(gf["in_elems"] * 2, device="cuda", generator=gen).to(torch.float16)
+        self.d_smp = torch.zeros(gf["out_elems"] * 2, device="cuda", dtype=torch.float16)
+        self.d_sos = torch.zeros(self.npix, device="cuda", dtype=torch.float32)
+        self.d_out = torch.zeros(self.npix * 2, device="cuda", dtype=torch.float32)
+        self.h_img = torch.empty(gf["in_elems"] * 2, dtype=torch.float16, pin_memory=True); self.h_img.copy_(self.d_img)
+        self.h_out = torch.empty(self.npix * 2, dtype=torch.float32, pin_memory=True)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.nsamp = 2 * nc * gf["nro"] * gf["npe1work"]                # forward + adjoint coil-samples, all ranks
+
+    def step(self, from_host=False, reduce=True):
+        if from_host:
+            self.d_img.copy_(self.h_img, non_blocking=True)
+        self.fw.recon_device(self.d_smp.data_ptr(), self.d_img.data_ptr(), self.stream)
+        self.ad.recon_device(self.d_sos.data_ptr(), self.d_smp.data_ptr(), self.stream)
+        if reduce:
+            self.comm.coil_reduce(self.d_out.data_ptr(), self.d_sos.data_ptr(), self.npix, root=0, stream=self.stream)
+        if from_host and self.rank == 0:
+            self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def reduce_only(self):
+        self.comm.coil_reduce(self.d_out.data_ptr(), self.d_sos.data_ptr(), self.npix, root=0, stream=self.stream)
+
+    def measure(self, steps, warmup):
+        torch, world = self.torch, self.world
+        ms = time_device(torch, lambda: self.step(False), steps, warmup, world)
+        ms_fw = time_device(torch, lambda: self.fw.recon_device(self.d_smp.data_ptr(), self.d_img.data_ptr(), self.stream), steps, 1, world)
+        ms_red = time_device(torch, self.reduce_only, max(steps, 5), 2, world)
+        e2e_ms = time_wall(torch, lambda: self.step(True), steps, 1, world)
+        gf, ga, ncl = self.gf, self.ga, self.ncl
+        n = gf["nxos"]
+        # SURVEY 8d: interpolation bytes of either direction with fp16 samples, f32 grid, per rank
+        b_dir = 4 * ncl * gf["nro"] * gf["npe1work"] + 8 * ncl * n * n
+        peak, peak_src = peak_hbm()
+        return {"value": self.nsamp / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "forward_ms": ms_fw,
+                "adjoint_plus_reduce_ms": ms - ms_fw, "reduce_ms": ms_red, "reduce_share_of_step": ms_red / ms,
+                "reduce_bytes": self.npix * 4, "coils_per_gpu": ncl, "n_gpus": world,
+                "gpu_launches_per_step": self.fw.last_launches() + self.ad.last_launches() + 1 + (1 if world > 1 else 0),
+                "e2e": {"value": self.nsamp / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": gf["in_elems"] * 4, "d2h_bytes_per_step": self.npix * 8},
+                "roofline": {"bound": "hbm (secondary: fp32, 36 flop/B at W = 6, SURVEY 8d)", "kernel": "degrid_wide + grid_wide (the two interpolation kernels' algorithmic bytes over the whole pair's time)",
+                             "achieved": 2 * b_dir / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": 2 * b_dir / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": 2 * b_dir}}
+
+    def image(self):
+        self.step(False)
+        self.torch.cuda.synchronize()
+        return self.d_out.clone()
+
+    def close(self):
+        self.fw.close(); self.ad.close()
+
+
+def make_comm(torch, t, rank, world, local):
+    """The library's NCCL communicator; torch.distributed only carries the 128-byte id (plumbing)."""
+    with _StdoutToStderr():
+        if world == 1:
+            return t.Comm(t.comm_unique_id(), 0, 1, local)
+        import torch.distributed as dist
+        buf = torch.zeros(t.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(t.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, src=0)
+        c = t.Comm(bytes(buf.cpu().numpy().tobytes()), rank, world, local)
+        torch.cuda.synchronize()
+        return c
+
+
+def cfg5_pipe_utilisation():
+    """FP32-pipe utilisation of the two cfg5 interpolation kernels, from the committed ncu capture."""
+    pj = os.path.join(ROOT, "profiles", "cfg5_pipe_util.json")
+    if os.path.isfile(pj):
+        try:
+            return json.load(open(pj))
+        except Exception:
+            return None
+    return None
+
+
+def strong_leg(torch, t, args, rank, world, local):
+    """ONE cfg2 acquisition, its 956 slices split over the ranks with slice_begin/slice_end: each rank
+    holds its window of the spokes (halo included) and writes its slab; no collective."""
+    dims, flags, desc = WORKLOADS["cfg2"]
+    nz = t.geometry(t.make_config(dims, **flags)).nz
+    lo, hi = t.shard_slices(nz, rank, world)
+    plan = t.Plan(t.make_config(dims, device=local, slices=(lo, hi), **flags))
+    g = plan.geom.as_dict()
+    d_in, h_in = make_input(torch, g["shard_in_elems"], 0)              # every rank: its stretch of a same-seeded stream
+    d_out = torch.zeros(g["shard_out_elems"] * 2, dtype=torch.float32, device="cuda")
+    h_out = torch.zeros(g["shard_out_elems"] * 2, dtype=torch.float32, pin_memory=True)
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = time_device(torch, lambda: plan.recon_device(d_out.data_ptr(), d_in.data_ptr(), stream), args.steps, args.warmup, world)
+    e2e_ms = time_wall(torch, lambda: plan.recon_host_ptr(h_out.data_ptr(), h_in.data_ptr()), args.steps, 1, world)
+    nsamp = g["nc"] * g["nro"] * g["npe1work"] * nz
+    plan.close()
+    return {"workload": "ONE cfg2 acquisition (956 slices) sharded by slice over %d GPUs, no collective" % world,
+            "scaling": "strong", "value": nsamp / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+            "slices_per_gpu": hi - lo,
+            "e2e": {"value": nsamp / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": g["shard_in_elems"] * 8, "d2h_bytes_per_step": g["shard_out_elems"] * 8}}
+
+
 def run_ours(args):
     import torch
     import tron_b200 as t
@@ -204,8 +601,10 @@ def run_ours(args):
     build.build()
     rank, world, local = dist_setup(args.gpus)
     dims, flags, desc = WORKLOADS[args.workload]
+    t_plan0 = time.perf_counter()
     cfg = t.make_config(dims, device=local, **flags)
     plan = t.Plan(cfg)
+    plan_create_ms = (time.perf_counter() - t_plan0) * 1e3
     g = plan.geom.as_dict()
     nsamp = g["nc"] * g["nro"] * g["npe1work"] * g["nz"]            # coil-samples gridded per step
     in_elems, out_elems = g["shard_in_elems"], g["shard_out_elems"]
@@ -235,47 +634,88 @@ def run_ours(args):
     checksum = float(d_out[::4097].double().abs().sum().item())
 
     # ---- end to end through the host-buffer C-ABI call
-    for _ in range(max(1, args.warmup // 2)):
-        plan.recon_host_ptr(h_out.data_ptr(), h_in.data_ptr())
-    barrier(world)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        plan.recon_host_ptr(h_out.data_ptr(), h_in.data_ptr())
+    e2e_s = time_wall(torch, lambda: plan.recon_host_ptr(h_out.data_ptr(), h_in.data_ptr()),
+                      args.steps, max(1, args.warmup // 2), world) * 1e-3
+    e2e_rel = rel_l2_t(h_out, d_out.cpu())
+    nz_local = g["slice_end"] - g["slice_begin"]
+    per_slice_rel = float(((h_out.view(nz_local, -1).double() - d_out.cpu().view(nz_local, -1).double()).norm(dim=1)
+                           / d_out.cpu().view(nz_local, -1).double().norm(dim=1).clamp_min(1e-300)).max().item())
+    floor_ms = copy_floor_ms(torch, h_in, d_in, h_out, d_out, args.steps, world)
+    plan.recon_device(d_out.data_ptr(), d_in.data_ptr(), stream)     # (the floor probe overwrote d_in/h_out with themselves: no-op)
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps, world)
-    barrier(world)
-    e2e_ok = bool(torch.equal(h_out[::4097], d_out[::4097].cpu()))
 
     # ---- roofline of the dominant kernel (gridding), timed alone on this stream
-    n, nc = g["nxos"], g["nc"]
     B = min(256, g["nz"])                                          # the launch length the device pipeline uses
-    d_grid = torch.empty(B * nc * n * n * 2, dtype=torch.float32, device="cuda")
-    nlaunch = 0
-    for z0 in range(0, min(g["nz"], 4 * B), B):                     # warm-up
-        plan.grid_device(d_grid.data_ptr(), d_in.data_ptr(), z0, min(B, g["nz"] - z0), stream)
-    torch.cuda.synchronize()
-    e0.record()
-    for z0 in range(0, g["nz"] - B + 1, B):
-        plan.grid_device(d_grid.data_ptr(), d_in.data_ptr(), z0, B, stream)
-        nlaunch += 1
-    e1.record()
-    torch.cuda.synchronize()
-    grid_ms = e0.elapsed_time(e1) / max(nlaunch, 1)
-    bytes_per_slice = 8 * nc * (g["nro"] * g["npe1work"] + n * n)
-    achieved = bytes_per_slice * B / (grid_ms * 1e-3) / 1e9
-    peak, peak_src = peak_hbm()
-    traffic = None
-    tj = os.path.join(ROOT, "profiles", "grid_traffic.json")
-    if os.path.isfile(tj):
-        try:
-            per_slice = json.load(open(tj)).get(args.workload + "_bytes_per_slice")
-            traffic = per_slice * B if per_slice else None
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "grid_gather_kernel (tron_grid_device, %d slices/launch)" % B,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_slice * B,
-                "ms_per_launch": grid_ms, "share_of_step": grid_ms * (g["nz"] / B) / ms_per_step}
+    kern = "grid_tile_kernel" if g["nc"] <= 8 else ("grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel")
+    roofline, grid_ms = grid_roofline(torch, plan, g, d_in, False, B, kern, args.workload)
+    roofline["share_of_step"] = grid_ms * (g["nz"] / B) / ms_per_step
+
+    extras = {}
+    if not args.lean and args.workload == "cfg2":
+        if world == 1:
+            # parity of THIS run's output against the unmodified reference (checker, untimed)
+            extras["parity"] = parity_vs_reference(torch, d_out, d_in, dims, flags, g, [0, 1, 31, 32, 477, 954, 955])
+            # cold span: what the reference's recon_radial2d brackets (tron.cu:726-786: init, buffers, recon,
+            # shutdown) through the same-named legacy symbol = plan create + recon + destroy per call
+            L = t.load_library()
+            assert L.tron_set_config(C.byref(cfg)) == 0
+            cold = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                L.recon_radial2d(C.c_void_p(h_out.data_ptr()), C.c_void_p(h_in.data_ptr()))
+                cold.append((time.perf_counter() - t0) * 1e3)
+            extras["e2e_cold"] = {"ms_per_step": float(np.median(cold)), "value": nsamp / (float(np.median(cold)) * 1e-3),
+                                  "unit": "samples/s", "runs_ms": cold, "plan_create_ms_first": plan_create_ms,
+                                  "how": "legacy recon_radial2d(h_out, h_in): tron_plan_create + tron_recon_host + "
+                                         "tron_plan_destroy per call, CUDA context already up (as in the reference arm)"}
+        plan.close(); plan = None
+        del d_in, d_out, h_in, h_out
+        torch.cuda.empty_cache()
+        if world == 1:
+            other = {}
+            for name, fn in (("cfg1", lambda: measure_cfg1(torch, t, local)),
+                             ("cfg3", lambda: measure_adjoint_config(torch, t, "cfg3", local, ref_slices=2)),
+                             ("cfg4", lambda: measure_adjoint_config(torch, t, "cfg4", local, ref_slices=16))):
+                try:
+                    other[name] = fn()
+                except Exception as e:           # an extra must never cost the headline line
+                    other[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.empty_cache()
+            try:
+                comm = make_comm(torch, t, rank, world, local)
+                pair = Cfg5Pair(torch, t, rank, world, local, comm)
+                c5 = pair.measure(3, 2)
+                c5["workload"] = "BASELINE cfg5: fp16-storage forward+adjoint pair, 1024 matrix, 2x grid, kernel width 6, 64 coils on one GPU"
+                c5["fp32_pipe"] = cfg5_pipe_utilisation()
+                pair.close(); comm.close()
+                fms, fhow = reference_chunks_ms([6, 1, 1024, 1024, 1], dict(kernwidth=6.0), 6, 64, adjoint=False)
+                ams, ahow = reference_chunks_ms([6, 1, 2048, 2048, 1], dict(kernwidth=6.0), 6, 64, adjoint=True)
+                if fms and ams:
+                    c5["reference_ms"] = fms + ams
+                    c5["reference_how"] = "one 6-coil chunk per direction through oracle/_ref (f32, its recon_radial2d span), scaled x64/6"
+                    c5["speedup_vs_reference_e2e"] = (fms + ams) / c5["e2e"]["ms_per_step"]
+                other["cfg5"] = c5
+            except Exception as e:
+                other["cfg5"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            extras["other_configs"] = other
+        else:
+            try:
+                extras["strong"] = strong_leg(torch, t, args, rank, world, local)
+            except Exception as e:
+                extras["strong"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            torch.cuda.empty_cache()
+            try:
+                comm = make_comm(torch, t, rank, world, local)
+                pair = Cfg5Pair(torch, t, rank, world, local, comm)
+                cs = pair.measure(args.steps, args.warmup)
+                cs["workload"] = ("BASELINE cfg5 pair, 64 coils sharded %d per GPU, partial sums of squares combined by "
+                                  "one ncclReduce (tron_coil_reduce) + sqrt on rank 0" % pair.ncl)
+                cs["scaling"] = "strong"
+                pair.close(); comm.close()
+                extras["coil_sharded"] = cs
+            except Exception as e:
+                extras["coil_sharded"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     out = None
     if rank == 0:
@@ -294,12 +734,17 @@ def run_ours(args):
                "e2e": {"value": nsamp * world / e2e_s, "unit": "samples/s", "ms_per_step": e2e_s * 1e3,
                        "images_per_s": g["nz"] * world / e2e_s,
                        "h2d_bytes_per_step": in_elems * 8, "d2h_bytes_per_step": out_elems * 8,
-                       "matches_device_path": e2e_ok},
+                       "rel_l2_vs_device": e2e_rel, "max_slice_rel_l2_vs_device": per_slice_rel,
+                       "copy_floor_ms": floor_ms, "frac_of_copy_floor": floor_ms / (e2e_s * 1e3),
+                       "copy_floor_how": "the step's H2D and D2H bytes alone, concurrently on two streams from the same "
+                                         "pinned buffers, max over ranks"},
                "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "checksum": checksum}
+        out.update(extras)
         if cpu:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)
-    plan.close()
+    if plan is not None:
+        plan.close()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -308,71 +753,27 @@ def run_ours(args):
 
 
 def run_cfg5(args):
-    """BASELINE cfg5: fp16-storage forward + adjoint NUFFT pair, 1024 matrix, 2x grid, kernel width 6,
-    64 coils sharded over the ranks; the coil root-sum-of-squares is one NCCL reduce of nx*ny floats.
-    Strong scaling: the 64 coils are split over the ranks (nc_local = 64 / N)."""
+    """BASELINE cfg5 as the main line (--workload cfg5): see Cfg5Pair."""
     import torch
     import tron_b200 as t
     from tron_b200 import build
     build.build()
     rank, world, local = dist_setup(args.gpus)
-    nc, nx = 64, 1024
-    ncl = nc // world
-    fw = t.Plan(t.make_config([ncl, 1, nx, nx, 1], adjoint=False, kernwidth=6.0, half_in=True, half_out=True, device=local))
-    gf = fw.geom.as_dict()
-    ad = t.Plan(t.make_config([ncl, 1, gf["nro"], gf["npe1work"], 1], adjoint=True, kernwidth=6.0, half_in=True,
-                              sos_partial=(ncl > 1), device=local))
-    ga = ad.geom.as_dict()
-    gen = torch.Generator(device="cuda"); gen.manual_seed(20261017 + 5 + 1000 * rank)
-    d_img = torch.randn(gf["in_elems"] * 2, device="cuda", generator=gen).to(torch.float16)
-    d_smp = torch.zeros(gf["out_elems"] * 2, device="cuda", dtype=torch.float16)
-    d_sos = torch.zeros(ga["nx"] * ga["ny"] * (1 if ncl > 1 else 2), device="cuda", dtype=torch.float32)
-    h_img = torch.empty(gf["in_elems"] * 2, dtype=torch.float16, pin_memory=True); h_img.copy_(d_img)
-    h_out = torch.empty(ga["nx"] * ga["ny"], dtype=torch.float32, pin_memory=True)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step(from_host):
-        if from_host:
-            d_img.copy_(h_img, non_blocking=True)
-        fw.recon_device(d_smp.data_ptr(), d_img.data_ptr(), stream)
-        ad.recon_device(d_sos.data_ptr(), d_smp.data_ptr(), stream)
-        if world > 1:
-            import torch.distributed as dist
-            dist.reduce(d_sos, dst=0, op=dist.ReduceOp.SUM)          # the one collective of the coil-sharded path
-        img = torch.sqrt(d_sos) if ncl > 1 else d_sos
-        if from_host:
-            h_out.copy_(img[: h_out.numel()], non_blocking=True)
-        return img
-
-    for _ in range(args.warmup):
-        step(False)
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step(False)
-    e1.record()
-    barrier(world)
-    ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
-    barrier(world)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(True)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps, world)
-    nsamp = 2 * nc * gf["nro"] * gf["npe1work"]                     # forward + adjoint coil-samples
+    comm = make_comm(torch, t, rank, world, local)
+    pair = Cfg5Pair(torch, t, rank, world, local, comm)
+    m = pair.measure(args.steps, args.warmup)
     if rank == 0:
-        print(json.dumps({"metric": "radial k-space samples gridded/sec", "value": nsamp / (ms * 1e-3), "unit": "samples/s",
-                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 storage)",
-                          "data": "synthetic",
-                          "config": {"workload": "BASELINE cfg5 fp16-storage forward+adjoint pair: 1024 matrix, 2x grid, "
-                                                 "kernel width 6, 64 coils coil-sharded, NCCL reduce of the partial sum of squares",
-                                     "name": "cfg5", "coils_per_gpu": ncl},
-                          "e2e": {"value": nsamp / e2e_s, "unit": "samples/s", "ms_per_step": e2e_s * 1e3,
-                                  "h2d_bytes_per_step": gf["in_elems"] * 4, "d2h_bytes_per_step": ga["nx"] * ga["ny"] * 4},
-                          "gpu_launches": (fw.last_launches() + ad.last_launches()) * args.steps}), flush=True)
-    fw.close(); ad.close()
+        line = {"metric": "radial k-space samples gridded/sec", "value": m["value"], "unit": "samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 storage)",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE cfg5 fp16-storage forward+adjoint pair: 1024 matrix, 2x grid, "
+                                       "kernel width 6, 64 coils coil-sharded, one ncclReduce of the partial sum of squares "
+                                       "(tron_coil_reduce)", "name": "cfg5", "coils_per_gpu": pair.ncl},
+                "e2e": m["e2e"], "gpu_launches": m["gpu_launches_per_step"] * args.steps, "roofline": m["roofline"],
+                "coil_sharded": m}
+        print(json.dumps(line), flush=True)
+    pair.close(); comm.close()
     if world > 1:
         import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()
@@ -444,6 +845,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--lean", action="store_true", help="headline line only: no parity / cold / other-config / strong / coil-sharded legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

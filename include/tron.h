@@ -150,6 +150,31 @@ int  tron_plan_last_launches(const tron_plan *plan);
 /* diagnostic (plan created with TRON_GRID_DEBUG set): per-warp cycle counts of the last gridding launch */
 int  tron_plan_grid_debug(tron_plan *plan, long long *h_cycles, int nwarps);
 
+/* ------------------------------------------------------------------ */
+/* Coil-sharded root sum of squares: the one collective of the path     */
+/* ------------------------------------------------------------------ */
+/* The reference combines the coils of a slice on one GPU (coilcombinesos, tron.cu:255-268, called at
+ * tron.cu:764) and has no communication at all (MULTI_GPU, tron.h:48-49, tron.cu:582-585).  With the coils
+ * of a slice sharded over GPUs (tron_config.coil_begin/coil_end + sos_partial) every GPU ends with
+ * float32[nx*ny] partial sums per slice; tron_coil_reduce is ONE ncclReduce(sum) of those to `root` over
+ * NVLink followed by sqrt on the root, which leaves the same (sqrt(sum), 0) complex64 pixels (complex-half
+ * with half_out) as tron.cu:263-264.  Asynchronous on `stream`; d_sos is used in place.
+ *
+ * One process per GPU: rank 0 fills 128 bytes with tron_comm_unique_id(), hands them to the other ranks
+ * (any launcher transport), each rank calls tron_comm_create().  One process for all GPUs:
+ * tron_comm_create_all() (ncclCommInitAll) and tron_coil_reduce_all() (one NCCL group). */
+typedef struct tron_comm tron_comm;
+#define TRON_COMM_ID_BYTES 128
+int  tron_comm_unique_id(void *id, size_t bytes);
+int  tron_comm_create(tron_comm **comm, const void *id, size_t bytes, int rank, int nranks, int device);
+int  tron_comm_create_all(tron_comm **comms, int ndev, const int *devices);
+int  tron_comm_destroy(tron_comm *comm);
+int  tron_comm_rank(const tron_comm *comm);
+int  tron_comm_size(const tron_comm *comm);
+int  tron_coil_reduce(tron_comm *comm, void *d_img, void *d_sos, size_t npix, int root, int half_out, void *stream);
+int  tron_coil_reduce_all(tron_comm **comms, int n, void *d_img_root, void **d_sos, size_t npix, int root,
+                          int half_out, void **streams);
+
 const char *tron_last_error(void);
 int  tron_version(void);
 

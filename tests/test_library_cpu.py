@@ -105,6 +105,9 @@ def test_geometry_rejections(lib):
         (dict(dims=[1, 1, 64, 64, 1], adjoint=False, niter=3), "CGNR"),       # tron.cu:753-755: adjoint only
         (dict(dims=[2, 1, 64, 64, 1], adjoint=True, niter=3, gridos=1.5), "CGNR"),   # needs nro == nxos
         (dict(dims=[4, 1, 64, 64, 1], adjoint=True, niter=2, coils=(0, 2)), "coil shards"),
+        (dict(dims=[4, 1, 64, 64, 1], adjoint=True, coils=(0, 2)), "sos_partial"),             # RSS of a partial sum
+        (dict(dims=[4, 1, 64, 64, 1], adjoint=True, coils=(0, 2), per_coil_out=True, sos_partial=True), "sos_partial"),
+        (dict(dims=[4, 1, 64, 64, 1], adjoint=False, coils=(2, 4)), "dims\\[0\\]"),                 # forward: shard the input
         (dict(dims=[4, 1, 64, 64, 1], adjoint=True, coil_combine=1, per_coil_out=True), "Walsh"),
         (dict(dims=[4, 1, 64, 64, 1], adjoint=True, coil_combine=2), "coil_combine"),
         (dict(dims=[1, 1, 64, 64, 1], adjoint=True, koosh=True), "koosh"),

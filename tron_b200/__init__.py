@@ -6,8 +6,8 @@ is the thin host-side binding used by the tests and bench.py.
 """
 from .api import (Config, Geometry, Plan, TronError, geometry, load_library, make_config, ra_read,
                   ra_write, recon_radial2d, shard_slices, coilcombine_walsh_device, coilcombine_sos_device,
-                  EXPORTED_SYMBOLS, LIB_PATH, CLI_PATH)
+                  EXPORTED_SYMBOLS, LIB_PATH, CLI_PATH, Comm, comm_unique_id, COMM_ID_BYTES)
 
 __all__ = ["Config", "Geometry", "Plan", "TronError", "geometry", "load_library", "make_config", "ra_read",
            "ra_write", "recon_radial2d", "shard_slices", "coilcombine_walsh_device", "coilcombine_sos_device",
-           "EXPORTED_SYMBOLS", "LIB_PATH", "CLI_PATH"]
+           "EXPORTED_SYMBOLS", "LIB_PATH", "CLI_PATH", "Comm", "comm_unique_id", "COMM_ID_BYTES"]

@@ -70,6 +70,9 @@ EXPORTED_SYMBOLS = [
     "tron_grid_to_interleaved", "tron_degrid_device", "tron_plan_last_stage_ms", "tron_plan_last_launches",
     "tron_plan_grid_debug", "tron_coilcombine_sos_device", "tron_coilcombine_walsh_device",
     "tron_last_error", "tron_version",
+    # tron.h: coil-sharded root sum of squares (NCCL)
+    "tron_comm_unique_id", "tron_comm_create", "tron_comm_create_all", "tron_comm_destroy", "tron_comm_rank",
+    "tron_comm_size", "tron_coil_reduce", "tron_coil_reduce_all",
     # tron.h: legacy surface
     "tron_set_config", "tron_init", "tron_shutdown", "tron_nufft_adj_radial2d", "tron_nufft_radial2d",
     "recon_radial2d", "recon_radial_2d", "gridradial2d", "degridradial2d",
@@ -114,6 +117,15 @@ def load_library(path=None):
     L.tron_plan_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tron_plan_last_launches.argtypes = [C.c_void_p]
     L.tron_set_config.argtypes = [C.POINTER(Config)]
+    L.tron_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    L.tron_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
+    L.tron_comm_create_all.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int)]
+    L.tron_comm_destroy.argtypes = [C.c_void_p]
+    L.tron_comm_rank.argtypes = [C.c_void_p]
+    L.tron_comm_size.argtypes = [C.c_void_p]
+    L.tron_coil_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    L.tron_coil_reduce_all.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t,
+                                       C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.recon_radial2d.argtypes = [C.c_void_p, C.c_void_p]
     L.recon_radial2d.restype = None
     L.tron_launch_gridradial2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
@@ -283,6 +295,43 @@ class Plan:
         ms = (C.c_float * 3)()
         _check(self.lib.tron_plan_last_stage_ms(self.handle, ms), self.lib)
         return [float(x) for x in ms]
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """128 opaque bytes rank 0 hands to every other rank (ncclGetUniqueId)."""
+    L = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(L.tron_comm_unique_id(buf, COMM_ID_BYTES), L)
+    return buf.raw
+
+
+class Comm:
+    """One rank's NCCL communicator for the coil-sharded sum of squares (include/tron.h: tron_comm_*)."""
+
+    def __init__(self, unique_id, rank, nranks, device):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        _check(self.lib.tron_comm_create(C.byref(self.handle), unique_id, len(unique_id), rank, nranks, device), self.lib)
+        self.rank, self.nranks = rank, nranks
+
+    def coil_reduce(self, d_img_ptr, d_sos_ptr, npix, root=0, half_out=False, stream=0):
+        """ncclReduce(sum) of float32[npix] partial sums of squares to `root`, then (sqrt, 0) pixels there."""
+        _check(self.lib.tron_coil_reduce(self.handle, C.c_void_p(d_img_ptr), C.c_void_p(d_sos_ptr), npix, root,
+                                         int(half_out), C.c_void_p(stream)), self.lib)
+
+    def close(self):
+        if self.handle:
+            self.lib.tron_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def coilcombine_walsh_device(d_img_ptr, d_coil_ptr, nimg, nchan, npatch=1, nslices=1, stream=0):

@@ -20,7 +20,7 @@ EXE = os.path.join(BINDIR, "tron")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "--use_fast_math", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "-w"] + ARCH
-CU_SOURCES = ["plan.cu", "grid.cu", "grid_tile.cu", "grid_wide.cu", "degrid.cu", "degrid_wide.cu", "fft.cu", "combine.cu", "cgnr.cu", "legacy.cu"]
+CU_SOURCES = ["plan.cu", "grid.cu", "grid_tile.cu", "grid_wide.cu", "degrid.cu", "degrid_wide.cu", "fft.cu", "combine.cu", "cgnr.cu", "legacy.cu", "comm.cu"]
 HOST_SOURCES = ["ra.c", "float16.cpp"]
 
 
@@ -81,7 +81,7 @@ def build(force=False, verbose=False, check_stale=False):
         log.append(out)
         if p.returncode != 0:
             raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), out))
-    _run(["nvcc", "-shared"] + ARCH + objs + ["-o", LIB])
+    _run(["nvcc", "-shared"] + ARCH + objs + ["-ldl", "-o", LIB])
     _run(["nvcc"] + NVCC_FLAGS + [os.path.join(CSRC, "tron_main.cu"), "-o", EXE,
                                   "-L" + LIBDIR, "-ltron_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib"])
     shutil.rmtree(objdir, ignore_errors=True)

@@ -114,6 +114,11 @@ extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
     int nch = g->coil_end - g->coil_begin;
     if (nch != g->nc && c->adjoint && (c->niter > 0 || c->coil_combine == 1)) { set_error("CGNR and the Walsh combine need every coil of a slice: coil shards are not supported"); return TRON_EUNSUPPORTED; }
     if (g->nc > 1 && ((g->coil_begin & 1) || (nch & 1))) { set_error("coil shards must start at an even channel and hold an even count"); return TRON_EINVAL; }
+    /* A shard of the coils writes only its own channels of a channel-interleaved output (forward samples,
+     * per-coil images) and cannot form the root of a partial sum: the one defined coil-sharded product is the
+     * partial sum of squares, reduced across GPUs by tron_coil_reduce (comm.cu).  A forward transform is
+     * coil-sharded by cutting dims[0] of its input instead (the channels are independent, tron.cu:540-577). */
+    if (nch != g->nc && !(c->adjoint && c->sos_partial && !c->per_coil_out)) { set_error("coil shards [%d,%d) of %d need adjoint + sos_partial (partial sum of squares for tron_coil_reduce); shard a forward transform by its input's dims[0]", g->coil_begin, g->coil_end, g->nc); return TRON_EUNSUPPORTED; }
 
     uint64_t spoke = (uint64_t)g->nc * g->nt * g->nro;
     if (c->adjoint) {
@@ -188,10 +193,12 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         set_error("no CUDA device: libtron_b200 has no CPU path");
         return TRON_ENODEV;
     }
-    if (cfg->device >= 0) {
-        if (cfg->device >= ndev) { set_error("device %d of %d", cfg->device, ndev); return TRON_ENODEV; }
-        TRON_CUDA(cudaSetDevice(cfg->device));                       /* -g, tron.cu:837-839 */
-    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cfg->device >= ndev) { set_error("device %d of %d", cfg->device, ndev); return TRON_ENODEV; }
+    /* -g (tron.cu:837-839) picks the plan's device; the caller's current device is restored on return
+     * (the CLI, like the reference's main(), selects it for the process itself) */
+    DeviceGuard guard(cfg->device >= 0 ? cfg->device : cur);
     tron_plan *p = new tron_plan();
     p->cfg = *cfg; p->g = g;
     cudaGetDevice(&p->device);
@@ -340,7 +347,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
 extern "C" int tron_plan_destroy(tron_plan *p)
 {
     if (!p) return TRON_OK;
-    cudaSetDevice(p->device);
+    DeviceGuard guard(p->device);
     cudaDeviceSynchronize();
     plan_release(p);
     return TRON_OK;
@@ -568,7 +575,7 @@ static int run_forward(tron_plan *p, void *d_out, const void *d_in, cudaStream_t
 extern "C" int tron_recon_device(tron_plan *p, void *d_out, const void *d_in, void *stream)
 {
     if (!p || !d_out || !d_in) { set_error("null argument"); return TRON_EINVAL; }
-    TRON_CUDA(cudaSetDevice(p->device));
+    DeviceGuard guard(p->device);
     cudaStream_t s = (cudaStream_t)stream;
     p->last_launches = 0;
     p->last_ms[0] = p->last_ms[1] = p->last_ms[2] = 0.f;
@@ -579,7 +586,7 @@ extern "C" int tron_recon_device(tron_plan *p, void *d_out, const void *d_in, vo
 extern "C" int tron_recon_host(tron_plan *p, void *h_out, const void *h_in)
 {
     if (!p || !h_out || !h_in) { set_error("null argument"); return TRON_EINVAL; }
-    TRON_CUDA(cudaSetDevice(p->device));
+    DeviceGuard guard(p->device);
     if (!p->d_in) TRON_CUDA(cudaMalloc(&p->d_in, p->in_bytes));
     if (!p->d_out) TRON_CUDA(cudaMalloc(&p->d_out, p->out_bytes));
     p->last_launches = 0;
@@ -600,7 +607,7 @@ extern "C" int tron_grid_device(tron_plan *p, void *d_grid, const void *d_sample
 {
     if (!p || !p->cfg.adjoint) { set_error("tron_grid_device needs an adjoint plan"); return TRON_EINVAL; }
     if (z0 < 0 || nslices < 1 || z0 + nslices > p->nslices) { set_error("slice range [%d,%d) outside the plan's %d slices", z0, z0 + nslices, p->nslices); return TRON_EINVAL; }
-    TRON_CUDA(cudaSetDevice(p->device));
+    DeviceGuard guard(p->device);
     cudaStream_t s = (cudaStream_t)stream;
     GridLaunch L = make_grid_launch(p, d_samples, (float2 *)d_grid, z0, nslices);
     return launch_grid(L, s);
@@ -609,7 +616,7 @@ extern "C" int tron_grid_device(tron_plan *p, void *d_grid, const void *d_sample
 extern "C" int tron_grid_to_interleaved(tron_plan *p, void *d_dst, const void *d_grid, int nslices, void *stream)
 {
     if (!p) { set_error("null plan"); return TRON_EINVAL; }
-    TRON_CUDA(cudaSetDevice(p->device));
+    DeviceGuard guard(p->device);
     cudaStream_t s = (cudaStream_t)stream;
     return launch_interleave((float2 *)d_dst, (const float2 *)d_grid, p->nch, p->g.nxos, nslices, s);
 }
@@ -617,7 +624,7 @@ extern "C" int tron_grid_to_interleaved(tron_plan *p, void *d_dst, const void *d
 extern "C" int tron_degrid_device(tron_plan *p, void *d_samples, const void *d_grid, void *stream)
 {
     if (!p || p->cfg.adjoint) { set_error("tron_degrid_device needs a forward plan"); return TRON_EINVAL; }
-    TRON_CUDA(cudaSetDevice(p->device));
+    DeviceGuard guard(p->device);
     cudaStream_t s = (cudaStream_t)stream;
     const tron_geometry &g = p->g;
     if (p->nch != g.nc) { set_error("tron_degrid_device does not support coil shards"); return TRON_EUNSUPPORTED; }

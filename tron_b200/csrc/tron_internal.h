@@ -16,6 +16,16 @@ int  cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 #define TRON_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
     return tronb::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
 
+/* Entry points run on the plan's device and leave the caller's current device as they found it
+ * (hosts such as torch keep their own notion of the current device). */
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (dev != prev) cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 /* One sorted-spoke table per slice group (golden angle) or one shared table (linear). */
 struct SpokeTables {
     float4 *cs = nullptr;     /* [ntab][npe]  (cos, sin, 1/cos, 1/sin), sorted by angle mod pi */
