@@ -11,7 +11,8 @@ from bench import WORKLOADS
 name = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 dims, flags, desc = WORKLOADS[name]
-KNOBS = ('TRON_NO_TILE', 'TRON_TILE_GPER', 'TRON_TILE_CAP', 'TRON_TILE_NEAR', 'TRON_TILE_MB', 'TRON_TILE_DELTA')
+KNOBS = ('TRON_NO_TILE', 'TRON_TILE_GPER', 'TRON_TILE_CAP', 'TRON_TILE_NEAR', 'TRON_TILE_MB', 'TRON_TILE_DELTA',
+         'TRON_NO_SCATTER', 'TRON_SCATTER_CHAIN', 'TRON_SCATTER_CHAIN_NEAR', 'TRON_SCATTER_NEAR', 'TRON_SCATTER_CAP')
 
 def run(env, check=None):
     for k in KNOBS:
@@ -46,7 +47,7 @@ def run(env, check=None):
                       'GBps': bytes_per_slice * b / best / 1e6, 'same_as_l1_kernel': same}), flush=True)
     return out
 
-ref = run({'TRON_NO_TILE': '1'})
+ref = run({'TRON_NO_TILE': '1', 'TRON_NO_SCATTER': '1'})
 variants = [dict(v.split('=') for v in a.split(',') if v) for a in sys.argv[3:]] or [
     {}, {'TRON_TILE_GPER': '4'}, {'TRON_TILE_GPER': '16'}, {'TRON_TILE_CAP': '8192'}, {'TRON_TILE_CAP': '16384'},
     {'TRON_TILE_NEAR': '16'}, {'TRON_TILE_NEAR': '64'}]

@@ -271,6 +271,7 @@ def test_tile_kernel_matches_l1_gather(lib, monkeypatch, nchan, half, flags, env
     for tile in (False, True):
         for k in ("TRON_NO_TILE", "TRON_TILE_CAP", "TRON_TILE_GPER", "TRON_TILE_NEAR", "TRON_TILE_DELTA"):
             monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv("TRON_NO_SCATTER", "1")
         if tile:
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
@@ -297,6 +298,62 @@ def test_tile_kernel_matches_l1_gather(lib, monkeypatch, nchan, half, flags, env
         empty = outs[0] == 0
         assert np.abs(outs[1][empty]).max() <= 1e-6 * np.abs(outs[0]).max()
         assert np.array_equal(outs[0][:1] != 0, outs[1][:1] != 0)          # the chain's first group is gridded in full
+
+
+@pytest.mark.parametrize("nchan,half,nro,flags,env", [
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {}),                                     # chains of differences (32 / 8 slices)
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_CHAIN": "1"}),            # every slice gridded in full
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_CHAIN": "5", "TRON_SCATTER_CHAIN_NEAR": "5"}),
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_NEAR": "2"}),             # no tile on the split path
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_NEAR": "0"}),             # every tile on the split path
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_CAP": "1536"}),           # many rounds per slice
+    (4, False, 128, dict(golden=True, undersamp=0.25, prof_slide=2, skip_angles=5), {}),
+    (2, False, 96, dict(golden=True, undersamp=0.5, prof_slide=2, skip_angles=11), {}),                       # 96^2 grid: 6 x 6 tiles
+    (4, False, 128, dict(golden=False, prof_slide=40, undersamp=0.4), {}),                                    # linear angles: one shared table
+    (6, False, 256, dict(golden=True), {}),                                                                   # one slice, 256^2
+    (6, True, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {}),                                      # fp16 storage: 24-byte samples
+    (2, True, 128, dict(golden=True, undersamp=0.3, prof_slide=5), {"TRON_SCATTER_CAP": "512"}),
+])
+def test_scatter_kernel_matches_l1_gather(lib, monkeypatch, nchan, half, nro, flags, env):
+    """grid_scatter.cu (tiles accumulated in shared memory, sample driven) applies the same taps with the same weights
+    as grid.cu (one thread per cell, taps through L1); the order of the additions differs, and with sliding-window
+    chains a slice is its predecessor plus / minus the spokes that entered / left."""
+    import tron_b200 as t
+    torch = torch_cuda()
+    npe1 = 150
+    s = synth_complex((npe1, nro, nchan), stream=95 + nchan)
+    raw = s.view(np.float32).astype(np.float16) if half else s.view(np.float32)
+    outs = []
+    for scatter in (False, True):
+        for k in ("TRON_NO_TILE", "TRON_NO_SCATTER", "TRON_SCATTER_CHAIN", "TRON_SCATTER_CHAIN_NEAR", "TRON_SCATTER_NEAR", "TRON_SCATTER_CAP"):
+            monkeypatch.delenv(k, raising=False)
+        if scatter:
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+        else:
+            monkeypatch.setenv("TRON_NO_TILE", "1")
+            monkeypatch.setenv("TRON_NO_SCATTER", "1")
+        with t.Plan(t.make_config([nchan, 1, nro, npe1, 1], adjoint=True, half_in=half, **flags)) as p:
+            ns, n = p.geom.nz, p.geom.nxos
+            d_s = torch.from_numpy(raw.copy()).cuda()
+            d_g = torch.full((ns, nchan, n, n, 2), 7.0, dtype=torch.float32, device="cuda")
+            p.grid_device(d_g.data_ptr(), d_s.data_ptr(), 0, ns, torch.cuda.current_stream().cuda_stream)
+            if ns > 3:                                     # a launch that starts and ends inside chains
+                d_g[1:ns - 1] = 7.0
+                p.grid_device(d_g[1:].data_ptr(), d_s.data_ptr(), 1, ns - 2, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            outs.append(d_g.cpu().numpy())
+    assert np.abs(outs[0]).max() > 0
+    chains = flags.get("golden") and flags.get("prof_slide", 0) not in (0, 40) and env.get("TRON_SCATTER_CHAIN") != "1"
+    per_slice = max(rel_l2(a, b) for a, b in zip(outs[1], outs[0]))
+    if not chains:
+        assert np.array_equal(outs[0] != 0, outs[1] != 0)
+        assert per_slice <= 2e-7, per_slice
+    else:
+        assert per_slice <= 5e-7, per_slice
+        empty = outs[0] == 0
+        assert np.abs(outs[1][empty]).max() <= 1e-6 * np.abs(outs[0]).max()
+        assert np.array_equal(outs[0][:1] != 0, outs[1][:1] != 0)          # a chain's first slice is gridded in full
 
 
 def _degrid_mine(t, torch, grid, n_img, nchan, **flags):

@@ -297,6 +297,10 @@ int launch_grid(const GridLaunch &g, cudaStream_t s)
     if (g.nslices <= 0 || g.nch <= 0) return 0;
     const bool no_wide = getenv("TRON_NO_WIDE") != nullptr;      /* diagnostic switch, read per launch */
     if (!no_wide && grid_wide_applicable(g)) return launch_grid_wide(g, s);   /* nc >= 16: lanes = channels */
+    if (aligned && grid_scatter_applicable(g)) {           /* tiles accumulated in shared memory, sample driven */
+        const int rc = launch_grid_scatter(g, s);
+        if (rc >= 0) return rc;
+    }
     if (aligned && grid_tile_applicable(g)) {              /* samples staged in shared memory by bulk copies */
         const int rc = launch_grid_tile(g, s);
         if (rc >= 0) return rc;                            /* < 0: geometry outside that kernel's limits */

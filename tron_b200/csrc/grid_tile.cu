@@ -36,15 +36,15 @@ namespace tronb {
 /* ---------------------------------------------------------------------- */
 /* plan-time: per-footprint angular window = union of its cells' windows   */
 /* ---------------------------------------------------------------------- */
-__global__ void foot_window_kernel(int2 *win, const int2 *cells, int n, int nbins, int nfx, int nfy)
+__global__ void foot_window_kernel(int2 *win, const int2 *cells, int n, int nbins, int nfx, int nfy, int fw, int fh)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nfx * nfy) return;
-    const int x0 = (t % nfx) * FOOT_W, y0 = (t / nfx) * FOOT_H;
+    const int x0 = (t % nfx) * fw, y0 = (t / nfx) * fh;
     bool any = false, all = false;
     int ref = 0, lo = 0, hi = 0;
-    for (int y = y0; y < y0 + FOOT_H && y < n; ++y)
-        for (int x = x0; x < x0 + FOOT_W && x < n; ++x) {
+    for (int y = y0; y < y0 + fh && y < n; ++y)
+        for (int x = x0; x < x0 + fw && x < n; ++x) {
             const int2 c = cells[(size_t)y * n + x];
             const int Rlo = c.x & 0xffff, Rhi = c.x >> 16;
             if (Rlo > Rhi) continue;
@@ -68,11 +68,12 @@ __global__ void foot_window_kernel(int2 *win, const int2 *cells, int n, int nbin
     win[t] = w;
 }
 
-int build_tile_windows(int2 **d_win, const int2 *cells, int n, int nbins, cudaStream_t s)
+/* windows of fw x fh footprints (8 x 4: one warp of grid_tile.cu; 16 x 16: one tile of grid_scatter.cu) */
+int build_tile_windows(int2 **d_win, const int2 *cells, int n, int nbins, int fw, int fh, cudaStream_t s)
 {
-    const int nfx = (n + FOOT_W - 1) / FOOT_W, nfy = (n + FOOT_H - 1) / FOOT_H;
+    const int nfx = (n + fw - 1) / fw, nfy = (n + fh - 1) / fh;
     TRON_CUDA(cudaMalloc(d_win, (size_t)nfx * nfy * sizeof(int2)));
-    foot_window_kernel<<<(nfx * nfy + 127) / 128, 128, 0, s>>>(*d_win, cells, n, nbins, nfx, nfy);
+    foot_window_kernel<<<(nfx * nfy + 127) / 128, 128, 0, s>>>(*d_win, cells, n, nbins, nfx, nfy, fw, fh);
     TRON_CUDA(cudaGetLastError());
     return 0;
 }
@@ -173,68 +174,6 @@ int build_tile_schedule(int **d_order, int *n_near, int n, int th, float near_r)
     return 0;
 }
 
-/* ---------------------------------------------------------------------- */
-/* shared-memory plumbing                                                  */
-/* ---------------------------------------------------------------------- */
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
-{
-    unsigned done;
-    do {
-        asm volatile("{\n.reg .pred p;\n"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                     "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-/* global -> shared bulk copy (TMA, no tensor map): 16-byte aligned addresses, size a multiple of 16 */
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ float4 lds_f4(unsigned a)
-{
-    float4 q;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(a));
-    return q;
-}
-__device__ __forceinline__ uint2 lds_u2(unsigned a)
-{
-    uint2 q;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(q.x), "=r"(q.y) : "r"(a));
-    return q;
-}
-
-/* CH channels of one staged sample */
-template <int CH, bool HALF>
-__device__ __forceinline__ void lds_sample(float2 (&v)[CH], unsigned a)
-{
-    static_assert(CH % 2 == 0, "staged samples are read in 16-byte (8-byte for fp16 storage) pieces");
-    if (!HALF) {
-#pragma unroll
-        for (int i = 0; i < CH / 2; ++i) {
-            float4 q = lds_f4(a + 16 * i);
-            v[2 * i] = make_float2(q.x, q.y); v[2 * i + 1] = make_float2(q.z, q.w);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < CH / 2; ++i) {
-            uint2 raw = lds_u2(a + 8 * i);
-            v[2 * i] = __half22float2(*reinterpret_cast<__half2 *>(&raw.x));
-            v[2 * i + 1] = __half22float2(*reinterpret_cast<__half2 *>(&raw.y));
-        }
-    }
-}
-
 #define TILE_ROUND_SLOTS 32
 struct alignas(128) WarpShared {       /* per warp; its two data buffers (cap bytes each) follow the descriptors of all warps */
     unsigned long long bar[2];
@@ -242,46 +181,6 @@ struct alignas(128) WarpShared {       /* per warp; its two data buffers (cap by
     float4 seg_a[2][TILE_ROUND_SLOTS]; /* cos, sin, 1/cos, 1/sin */
     float4 seg_b[2][TILE_ROUND_SLOTS]; /* W/|cos| + margin, W/|sin| + margin, bits: shared address of sample r = 0, bits: slice mask */
 };
-
-struct TileWindow { int k0, cnt; };
-
-/* window [k0, k0 + cnt) of the sorted table (stored twice: never wraps) for a packed bin window */
-__device__ __forceinline__ TileWindow window_of(int2 w, const int *__restrict__ lut, int nbins, int npe)
-{
-    TileWindow r; r.k0 = 0; r.cnt = npe;
-    if (w.x != CELL_ALL_SPOKES) {
-        int b0 = w.x, b1 = w.y;
-        if (b1 < b0) { r.cnt = 0; return r; }
-        bool wrap = false;
-        if (b1 >= nbins) { b1 -= nbins; wrap = true; }
-        const int ks = __ldg(lut + b0), ke = __ldg(lut + b1 + 1);
-        r.k0 = ks;
-        r.cnt = wrap ? (npe - ks) + ke : ke - ks;
-    }
-    return r;
-}
-
-/* 1/c and W/|c| + margin for the candidate run r in (X - W, X + W)/c = X/c -+ W/|c|; a vanishing cosine
- * or sine leaves the run unbounded on that axis (the reference predicate decides) */
-__device__ __forceinline__ void axis_terms(float c, float W, float &ic, float &hw)
-{
-    if (fabsf(c) < 1e-30f) { ic = 0.f; hw = 1e30f; }
-    else { ic = rcp_approx(c); hw = fmaf(W, fabsf(ic), 1e-3f); }
-}
-
-/* KB(dx) KB(dy): kb_poly_xy (refmath.cuh) with its instructions pinned behind the sample loads */
-__device__ __forceinline__ float kb_poly_xy_pinned(float dx, float dy, float invW, const unsigned long long (&c2)[TRONB_KB_DEG + 1])
-{
-    const float qx = dx * invW, qy = dy * invW;
-    float2 u = make_float2(fmaf(-qx, qx, 1.0f), fmaf(-qy, qy, 1.0f));
-    const unsigned long long U = *reinterpret_cast<unsigned long long *>(&u);
-    unsigned long long p = c2[TRONB_KB_DEG];
-#pragma unroll
-    for (int m = TRONB_KB_DEG - 1; m >= 0; --m)
-        asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p) : "l"(U), "l"(c2[m]));
-    const float2 r = *reinterpret_cast<float2 *>(&p);
-    return r.x * r.y;
-}
 
 /* the warp's staging cursor over (group, slot) */
 struct StageCursor { int grp, slot, k0, cnt; };
@@ -502,7 +401,7 @@ grid_tile_kernel(const GridLaunch g, const int2 *__restrict__ foot_win, const in
                     if (!(fabsf(dy) < Wk)) continue;
                     float2 v[CH];
                     lds_sample<CH, HALF>(v, (unsigned)(off + r * (int)SAMP));
-                    float w = kb_poly_xy_pinned(dx, dy, invW, c2);
+                    float w = kb_poly_xy_c2(dx, dy, invW, c2);
                     const float sdc = fmaf(sdc_as, fabsf(rf), sdc_bs);       /* tron.cu:412, times the output scale */
                     w *= (r == 0) ? sdc + sdc : sdc;       /* both of the reference's loops visit r = 0 */
                     if (GS > 1) w = __int_as_float(__float_as_int(w) ^ (mask & (int)0x80000000));   /* leaving spoke */

@@ -139,6 +139,7 @@ static void plan_release(tron_plan *p)
 {
     if (!p) return;
     cudaFree(p->tabs_d.gx); cudaFree(p->tabs_d.lut);
+    scatter_plan_free(p->scat);
     cudaFree(p->tabs.cs); cudaFree(p->tabs.pe); cudaFree(p->tabs.gx); cudaFree(p->tabs.lut); cudaFree(p->tabs.cs_lin); cudaFree(p->tabs.cells);
     fft_plan_free(p->fft);
     cudaFree(p->deapod_adj); cudaFree(p->deapod_fwd); cudaFree(p->tile_order); cudaFree(p->tile_order8); cudaFree(p->tile_order_rows); cudaFree(p->tile_order8_rows); cudaFree(p->heavy_cells); cudaFree(p->heavy_cells_big); cudaFree(p->grid_dbg); cudaFree(p->tile_win8); cudaFree(p->tile_sched8);
@@ -278,7 +279,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
             p->heavy_big = (double)n * n * ((per_launch + gsz - 1) / gsz) >= 2.0e6;
             if (getenv("TRON_HEAVY_BIG")) p->heavy_big = atoi(getenv("TRON_HEAVY_BIG")) != 0;
         }
-        PLAN_TRY(build_tile_windows(&p->tile_win8, p->tabs.cells, n, p->tabs.nbins, p->stream));
+        PLAN_TRY(build_tile_windows(&p->tile_win8, p->tabs.cells, n, p->tabs.nbins, 8, 4, p->stream));
         /* sliding windows: all but the first slice group of a chain are gridded from what enters and leaves
          * the window (grid_tile.cu); worth it when that is clearly fewer spokes than a group's union window */
         {
@@ -293,6 +294,16 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
                                             g.prof_slide, gsz, p->nslices, p->stream));
             }
         }
+        /* tiles accumulated in shared memory, sample driven (grid_scatter.cu): the default where it applies */
+        {
+            const bool fits = p->kb.fast && cfg->kernwidth == 2.0f && g.nro == g.nxos && p->nch == g.nc
+                              && (g.nc == 2 || g.nc == 4 || g.nc == 6) && n % 16 == 0 && n <= 4096 && g.npe1work <= 4096;
+            if (fits && !getenv("TRON_NO_SCATTER")) {
+                const int skip = cfg->skip_angles + (cfg->golden_angle ? g.slice_begin * g.prof_slide : 0);
+                PLAN_TRY(scatter_plan_build(p->scat, p->tabs.cells, p->tabs.nbins, n, p->nslices, g.npe1work, g.prof_slide,
+                                            skip, cfg->golden_angle, cfg->kernwidth, p->stream));
+            }
+        }
         PLAN_TRY(build_tile_schedule(&p->tile_sched8, &p->n_near8, n, 8,
                                      getenv("TRON_TILE_NEAR") ? (float)atof(getenv("TRON_TILE_NEAR")) : 32.f));
     }
@@ -302,7 +313,8 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
 
     p->batch = cfg->adjoint ? pick_batch(p) : 1;
     if (cfg->adjoint && p->tabs.gs > 1) {                /* launches start on group (chain) boundaries */
-        const int q = p->tabs.gs * (p->chain > 0 ? p->chain : 1);
+        int q = p->tabs.gs * (p->chain > 0 ? p->chain : 1);
+        if (p->scat.ready && p->scat.chain > q) q = p->scat.chain;
         p->batch = ((p->batch + q - 1) / q) * q;
     }
     p->stage_timing = getenv("TRON_STAGE_TIMING") != nullptr;
@@ -372,6 +384,7 @@ GridLaunch make_grid_launch(const tron_plan *p, const void *d_samples, float2 *d
     if (p->heavy_big) { L.heavy_cells = p->heavy_cells_big; L.nheavy = p->nheavy_big; L.heavy_r2 = p->heavy_r2_big; }
     else { L.heavy_cells = p->heavy_cells; L.nheavy = p->nheavy; L.heavy_r2 = p->heavy_r2; }
     L.tile_win8 = p->tile_win8; L.tile_sched8 = p->tile_sched8; L.n_near8 = p->n_near8;
+    L.scat = p->scat.ready ? &p->scat : nullptr;
     L.tab_gx_d = p->tabs_d.gx; L.lut_d = p->tabs_d.lut; L.npe_d = p->tabs_d.npe; L.chain = p->chain;
     L.heavy_cells_big = p->heavy_cells_big; L.nheavy_big = p->nheavy_big; L.heavy_r2_big = p->heavy_r2_big;
     L.tab_per_slice = p->tabs.ntab > 1 ? 1 : 0;
@@ -463,7 +476,8 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     const size_t grid_elems = (size_t)p->batch * p->nch * g.nxos * g.nxos;
     size_t spokes_up = 0;
     int i = 0;
-    const int gs = (p->tabs.gs > 0 ? p->tabs.gs : 1) * (p->chain > 0 ? p->chain : 1);   /* launch granularity */
+    int gs = (p->tabs.gs > 0 ? p->tabs.gs : 1) * (p->chain > 0 ? p->chain : 1);   /* launch granularity */
+    if (p->scat.ready && p->scat.chain > gs) gs = p->scat.chain;
     /* TRON_HOST_TRACE: when did the last upload, the last kernel and the last download finish? */
     static const bool trace = getenv("TRON_HOST_TRACE") != nullptr;
     cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -40,6 +40,19 @@ struct SpokeTables {
     int gs = 1;               /* slices per group */
 };
 
+/* grid_scatter.cu: per-slice sorted spoke tables (full window / difference from the previous slice), 16 x 16 tile
+ * windows and the tile schedule.  Device pointers + scalars: passed to the kernel by value. */
+struct ScatterPlan {
+    float4 *tab_full = nullptr; int *lut_full = nullptr;     /* [ntab][2*win], [ntab][nbins+1]; ntab = slices (golden) or 1 */
+    float4 *tab_delta = nullptr; int *lut_delta = nullptr;   /* [slices][2*ne_delta], ...; null: no difference tables */
+    int2 *tile_win = nullptr;                                /* packed angular-bin window per tile */
+    int *sched = nullptr;                                    /* tiles (ty << 16 | tx): n_near, then n_far, then ntiles_empty */
+    int win = 0, ne_delta = 0, per_slice = 0;
+    int chain = 1, chain_near = 1;                           /* slices per chain for far / near tiles */
+    int n_near = 0, n_far = 0, ntiles_empty = 0;
+    int ready = 0;
+};
+
 struct GridLaunch {               /* everything the gridding kernel needs */
     const void *samples;          /* first spoke of shard-local slice 0 */
     float2 *grid;                 /* [nslices][nch][n][n] */
@@ -66,6 +79,7 @@ struct GridLaunch {               /* everything the gridding kernel needs */
     const int2 *tile_win8 = nullptr;   /* grid_tile.cu: per 8x4 warp footprint, packed angular-bin window (union of its cells) */
     const int *tile_sched8 = nullptr;  /* grid_tile.cu: tile schedule, the n_near8 tiles next to DC first */
     int n_near8 = 0;
+    const ScatterPlan *scat = nullptr; /* grid_scatter.cu (host pointer; the launcher passes the struct by value) */
     int zero_r2;                  /* cells with X^2 + Y^2 > zero_r2 can hold no sample and are NOT stored (the FFT pass
                                      that follows does not fetch them); INT_MAX: every cell is stored */
 };
@@ -84,10 +98,15 @@ struct DegridLaunch {
 int launch_grid(const GridLaunch &g, cudaStream_t s);
 bool grid_tile_applicable(const GridLaunch &g);
 int launch_grid_tile(const GridLaunch &g, cudaStream_t s);
-int build_tile_windows(int2 **d_win, const int2 *cells, int n, int nbins, cudaStream_t s);
+int build_tile_windows(int2 **d_win, const int2 *cells, int n, int nbins, int fw, int fh, cudaStream_t s);
 int build_tile_schedule(int **d_order, int *n_near, int n, int th, float near_r);
 int build_delta_tables(SpokeTables &d, const SpokeTables &full, int ntab, int tab_stride, int skip, int win,
                        int slide, int gs, int nslices, cudaStream_t s);
+bool grid_scatter_applicable(const GridLaunch &g);
+int launch_grid_scatter(const GridLaunch &g, cudaStream_t s);
+int scatter_plan_build(ScatterPlan &sp, const int2 *cells, int nbins, int n, int nslices, int win, int slide, int skip,
+                       int golden, float W, cudaStream_t s);
+void scatter_plan_free(ScatterPlan &sp);
 bool grid_wide_applicable(const GridLaunch &g);
 int launch_grid_wide(const GridLaunch &g, cudaStream_t s);
 int launch_degrid(const DegridLaunch &d, cudaStream_t s);
@@ -182,6 +201,7 @@ struct tron_plan {
     int heavy_big = 0;                   /* which of the two lists this plan's launches use (fixed per plan: one summation order) */
     int2 *tile_win8 = nullptr; int *tile_sched8 = nullptr; int n_near8 = 0;   /* grid_tile.cu */
     tronb::SpokeTables tabs_d;           /* grid_tile.cu: sliding-window difference tables (empty: not in use) */
+    tronb::ScatterPlan scat;             /* grid_scatter.cu: tiles accumulated in shared memory (not ready: not in use) */
     int chain = 0;                       /* slice groups per chain: the first is gridded in full, the others from differences */
     int zero_r2 = 0x7fffffff;            /* adjoint: cells beyond this squared radius never receive a sample */
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
