@@ -12,7 +12,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 dims, flags, desc = WORKLOADS[name]
 KNOBS = ('TRON_NO_TILE', 'TRON_TILE_GPER', 'TRON_TILE_CAP', 'TRON_TILE_NEAR', 'TRON_TILE_MB', 'TRON_TILE_DELTA',
-         'TRON_NO_SCATTER', 'TRON_SCATTER_CHAIN', 'TRON_SCATTER_CHAIN_NEAR', 'TRON_SCATTER_NEAR', 'TRON_SCATTER_CAP')
+         'TRON_NO_SCATTER', 'TRON_SCATTER_CHAIN', 'TRON_SCATTER_CHAIN_NEAR', 'TRON_SCATTER_NEAR', 'TRON_SCATTER_CAP',
+         'TRON_SCATTER_SHORT_BELOW', 'TRON_SCATTER_CHAIN_SHORT', 'TRON_SCATTER_CHAIN_NEAR_SHORT', 'TRON_SCATTER_NEAR_SHORT')
 
 def run(env, check=None):
     for k in KNOBS:

@@ -377,3 +377,100 @@ def test_cgnr_single_coil_complex_output(lib, oracle, reflib):
         got_w = p.recon_host(h_in)
     assert np.abs(got.imag).max() > 0 and rel_l2(got, want) <= 1e-4
     assert np.array_equal(got, got_w)
+
+
+# ------------------------------------------------------------------ CGNR pinned to the reference's operators
+def _dense_operators_from_reference_kernels(reflib, nx, nro, npe, W=2.0):
+    """Dense matrices of the two operators the CGNR iterates with, one coil, built by pushing indicator vectors
+    through the REFERENCE's own kernels (oracle/_ref: gridradial2d tron.cu:465-536, degridradial2d 540-577,
+    deapodkernel 390-402); the stages between them are the exact linear maps the reference's host code applies
+    (pad 435-457, fftshift 161-178 = circular shift by n/2 for even n, unnormalised cuFFT, crop 418-431).
+      A (nsamp x npix): pad -> deapod(nxos, sigma 1) -> shift -> FFT forward -> shift -> degridradial2d   (639-649)
+      B (npix x nsamp): precompensate ramp -> gridradial2d -> shift -> FFT inverse -> shift -> deapod(nxos, sigma 1)
+                        -> crop, row 0 / column 0 cleared, sample ro = 0 dropped    (623-637, repaired: DESIGN 3.6)"""
+    n = 2 * nx
+    w = (n - nx) // 2
+    npix, nsamp = nx * nx, npe * nro
+    ones = np.ones((n, n, 1), dtype=np.complex64)
+    dw = reflib.deapod(ones, n, 1, W, 1.0)[:, :, 0].astype(np.complex128)        # what deapodkernel multiplies by
+    shift = lambda a: np.roll(a, (n // 2, n // 2), axis=(0, 1))
+    A = np.zeros((nsamp, npix), dtype=np.complex128)
+    for j0 in range(0, npix, 6):
+        cols = list(range(j0, min(j0 + 6, npix)))
+        u = np.zeros((n, n, 6), dtype=np.complex128)
+        for c, j in enumerate(cols):
+            row, col = divmod(j, nx)
+            if row > 0 and col > 0:                                            # pad drops source row 0 / column 0 (449-450)
+                u[row + w, col + w, c] = 1.0
+        u *= dw[:, :, None]
+        u = shift(np.fft.fft2(shift(u), axes=(0, 1)))
+        s = reflib.degrid(u.astype(np.complex64), n, 6, nro, npe, W=W, gridos=2.0, skip=0, golden=True)
+        for c, j in enumerate(cols):
+            A[:, j] = s[:, :, c].reshape(-1)
+    a = (2.0 - 2.0 / npe) / nro
+    b = 1.0 / npe
+    B = np.zeros((npix, nsamp), dtype=np.complex128)
+    for i0 in range(0, nsamp, 6):
+        rows = list(range(i0, min(i0 + 6, nsamp)))
+        s = np.zeros((npe, nro, 6), dtype=np.complex64)
+        for c, i in enumerate(rows):
+            pe, ro = divmod(i, nro)
+            if ro != 0:                                                        # M: ro = 0 is never gridded (Rhi <= nxos/2 - 1, 499)
+                s[pe, ro, c] = np.float32(a) * abs(np.float32(ro) - np.float32(nro // 2)) + np.float32(b)   # 405-416
+        g = reflib.grid(s, n, 6, nro, npe, W=W, gridos=2.0, skip=0, golden=True).astype(np.complex128)
+        g = shift(np.fft.ifft2(shift(g), axes=(0, 1)) * (n * n))
+        g = g * dw[:, :, None]
+        img = g[w:w + nx, w:w + nx, :].copy()
+        img[0, :, :] = 0
+        img[:, 0, :] = 0
+        for c, i in enumerate(rows):
+            B[:, i] = img[:, :, c].reshape(-1)
+    return A, B
+
+
+@pytest.mark.parametrize("niter", [1, 2, 3, 5])
+def test_cgnr_pinned_to_reference_operators_and_textbook_solver(lib, reflib, niter):
+    """The reference's own tron_cgnr_radial2d is self-declared broken (tron.cu:670), so the pin has two legs that do
+    not involve this repository's arithmetic: the OPERATORS are dense matrices assembled from the reference's
+    kernels, the ITERATION is textbook CGNR (Knopp et al. 2007, Alg. 1, the algorithm tron.cu:665-720 names) in
+    NumPy float64 on those matrices.  `tron -i niter` must agree to 1e-4."""
+    import tron_b200 as t
+    torch_cuda()
+    nc, nx, npe = 2, 12, 20
+    nro = 2 * nx
+    A, B = _dense_operators_from_reference_kernels(reflib, nx, nro, npe)
+    y = synth_complex((npe, nro, nc), stream=900).astype(np.complex128)
+    s = 1.0 / (2 * nx) / npe                                                   # the adjoint's output scale (532), inside B
+    wa, wb = (2.0 - 2.0 / npe) / nro, 1.0 / npe
+    ro = np.arange(nro)
+    Wp = wa * np.abs(ro - nro // 2) + wb                                       # the weights gridding really applies
+    Wp[nro // 2] *= 2.0                                                        # r = 0 visited twice (512, 521)
+    Wp[0] = 0.0
+    Wfull = np.tile(Wp, npe)
+    keep = np.tile((ro != 0).astype(np.float64), npe)                          # M
+    r = [y[:, :, c].reshape(-1) * keep for c in range(nc)]
+    z = [B @ rc for rc in r]
+    p = [zc.copy() for zc in z]
+    x = [np.zeros(nx * nx, dtype=np.complex128) for _ in range(nc)]
+    zz = sum(np.vdot(zc, zc).real for zc in z)
+    for it in range(niter):
+        v = [A @ pc for pc in p]
+        vwv = sum(np.sum(Wfull * np.abs(vc) ** 2) for vc in v)
+        alpha = zz / (s * vwv)
+        x = [xc + alpha * pc for xc, pc in zip(x, p)]
+        if it == niter - 1:
+            break
+        r = [rc - alpha * keep * vc for rc, vc in zip(r, v)]
+        z = [B @ rc for rc in r]
+        zz2 = sum(np.vdot(zc, zc).real for zc in z)
+        beta = zz2 / zz
+        p = [zc + beta * pc for zc, pc in zip(z, p)]
+        zz = zz2
+    want = np.stack([xc.reshape(nx, nx) for xc in x], axis=-1)
+    dims = [nc, 1, nro, npe, 1]
+    with t.Plan(t.make_config(dims, adjoint=True, golden=True, niter=niter, per_coil_out=True)) as pl:
+        got = pl.recon_host(y.astype(np.complex64)).reshape(nx, nx, nc)
+    assert rel_l2(got, want) <= 1e-4, rel_l2(got, want)
+    # the operator pair itself: B is s A^H W' up to the annulus clipping of gridding (DESIGN 3.6: < 1e-2 here)
+    asym = np.linalg.norm(B - s * (A.conj().T * Wfull[None, :])) / np.linalg.norm(B)
+    assert asym < 5e-2, asym

@@ -301,11 +301,14 @@ def test_tile_kernel_matches_l1_gather(lib, monkeypatch, nchan, half, flags, env
 
 
 @pytest.mark.parametrize("nchan,half,nro,flags,env", [
-    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {}),                                     # chains of differences (32 / 8 slices)
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {}),                                     # short-launch schedule: chains of 16 / 8 slices
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_SHORT_BELOW": "0"}),      # long-launch schedule: chains of 32 / 16
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_SHORT_BELOW": "0", "TRON_SCATTER_CHAIN": "6", "TRON_SCATTER_CHAIN_NEAR": "3"}),
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_CHAIN_SHORT": "4", "TRON_SCATTER_CHAIN_NEAR_SHORT": "2", "TRON_SCATTER_NEAR_SHORT": "0.3"}),
     (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_CHAIN": "1"}),            # every slice gridded in full
-    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_CHAIN": "5", "TRON_SCATTER_CHAIN_NEAR": "5"}),
-    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_NEAR": "2"}),             # no tile on the split path
-    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_NEAR": "0"}),             # every tile on the split path
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_SHORT_BELOW": "0", "TRON_SCATTER_CHAIN": "5", "TRON_SCATTER_CHAIN_NEAR": "5"}),
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_NEAR_SHORT": "2"}),       # no tile on the split path
+    (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_NEAR_SHORT": "0"}),       # every tile on the split path
     (6, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_CAP": "1536"}),           # many rounds per slice
     (4, False, 128, dict(golden=True, undersamp=0.25, prof_slide=2, skip_angles=5), {}),
     (2, False, 96, dict(golden=True, undersamp=0.5, prof_slide=2, skip_angles=11), {}),                       # 96^2 grid: 6 x 6 tiles
@@ -325,7 +328,8 @@ def test_scatter_kernel_matches_l1_gather(lib, monkeypatch, nchan, half, nro, fl
     raw = s.view(np.float32).astype(np.float16) if half else s.view(np.float32)
     outs = []
     for scatter in (False, True):
-        for k in ("TRON_NO_TILE", "TRON_NO_SCATTER", "TRON_SCATTER_CHAIN", "TRON_SCATTER_CHAIN_NEAR", "TRON_SCATTER_NEAR", "TRON_SCATTER_CAP"):
+        for k in ("TRON_NO_TILE", "TRON_NO_SCATTER", "TRON_SCATTER_CHAIN", "TRON_SCATTER_CHAIN_NEAR", "TRON_SCATTER_NEAR", "TRON_SCATTER_CAP",
+                  "TRON_SCATTER_SHORT_BELOW", "TRON_SCATTER_CHAIN_SHORT", "TRON_SCATTER_CHAIN_NEAR_SHORT", "TRON_SCATTER_NEAR_SHORT"):
             monkeypatch.delenv(k, raising=False)
         if scatter:
             for k, v in env.items():

@@ -124,8 +124,46 @@ static int build_scatter_table(float4 **gx, int **lut, int ntab, int ne, int kin
 void scatter_plan_free(ScatterPlan &sp)
 {
     cudaFree(sp.tab_full); cudaFree(sp.lut_full); cudaFree(sp.tab_delta); cudaFree(sp.lut_delta);
-    cudaFree(sp.tile_win); cudaFree(sp.sched);
+    cudaFree(sp.tile_win); cudaFree(sp.sched); cudaFree(sp.sched_short);
     sp = ScatterPlan();
+}
+
+/* tile schedule: nearest DC first; tiles whose angular window holds at least `near_frac` of all spokes are
+ * "near": one block (4 warps splitting the spokes) per tile and short chain.  order = near | far | empty. */
+static int build_scatter_schedule(int **d_sched, int *n_near, int *n_far, int *n_empty, const int2 *d_tile_win, int n,
+                                  int nbins, float W, float near_frac)
+{
+    const int nt1 = (n + SC_T - 1) / SC_T, nt = nt1 * nt1;
+    std::vector<int2> hw(nt);
+    TRON_CUDA(cudaMemcpy(hw.data(), d_tile_win, nt * sizeof(int2), cudaMemcpyDeviceToHost));
+    const float rz = (float)(n / 2 - 1) + W + 0.5f;            /* beyond: no cell can hold a sample */
+    std::vector<std::pair<float, int>> nearv, farv;
+    std::vector<int> empty;
+    for (int t = 0; t < nt; ++t) {
+        const int x0 = (t % nt1) * SC_T - n / 2, y0 = (t / nt1) * SC_T - n / 2;
+        const float dx = x0 > 0 ? (float)x0 : (x0 + SC_T - 1 < 0 ? (float)-(x0 + SC_T - 1) : 0.f);
+        const float dy = y0 > 0 ? (float)y0 : (y0 + SC_T - 1 < 0 ? (float)-(y0 + SC_T - 1) : 0.f);
+        const float d2 = dx * dx + dy * dy;
+        const int packed = ((t / nt1) << 16) | (t % nt1);
+        const int2 w = hw[t];
+        if (w.x != CELL_ALL_SPOKES && w.y < w.x) {             /* no cell of the tile is ever tapped: only zeros to store */
+            if (d2 <= rz * rz) farv.push_back(std::make_pair(d2, packed));
+            else empty.push_back(packed);                      /* beyond the last annulus: visited only when every cell is stored */
+            continue;
+        }
+        const float frac = w.x == CELL_ALL_SPOKES ? 1.f : (float)(w.y - w.x + 1) / (float)nbins;
+        if (frac >= near_frac) nearv.push_back(std::make_pair(d2, packed)); else farv.push_back(std::make_pair(d2, packed));
+    }
+    std::sort(nearv.begin(), nearv.end());
+    std::sort(farv.begin(), farv.end());
+    std::vector<int> order;
+    for (size_t i = 0; i < nearv.size(); ++i) order.push_back(nearv[i].second);
+    for (size_t i = 0; i < farv.size(); ++i) order.push_back(farv[i].second);
+    order.insert(order.end(), empty.begin(), empty.end());
+    *n_near = (int)nearv.size(); *n_far = (int)farv.size(); *n_empty = (int)empty.size();
+    TRON_CUDA(cudaMalloc(d_sched, order.size() * sizeof(int)));
+    TRON_CUDA(cudaMemcpy(*d_sched, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
 }
 
 /* `cells` / `nbins`: the per-cell table of the plan's spoke tables (slice independent), shared with the gather kernels */
@@ -154,46 +192,24 @@ int scatter_plan_build(ScatterPlan &sp, const int2 *cells, int nbins, int n, int
     }
     rc = build_tile_windows(&sp.tile_win, cells, n, nbins, SC_T, SC_T, s);
     if (rc) return rc;
-    /* tile schedule: nearest DC first; tiles whose angular window holds at least `near_frac` of all spokes are
-     * "near": one block (4 warps splitting the spokes) per tile and short chain */
-    const int nt1 = (n + SC_T - 1) / SC_T, nt = nt1 * nt1;
-    std::vector<int2> hw(nt);
-    TRON_CUDA(cudaStreamSynchronize(s));
-    TRON_CUDA(cudaMemcpy(hw.data(), sp.tile_win, nt * sizeof(int2), cudaMemcpyDeviceToHost));
     const float near_frac = getenv("TRON_SCATTER_NEAR") ? (float)atof(getenv("TRON_SCATTER_NEAR")) : 0.25f;
-    const float rz = (float)(n / 2 - 1) + W + 0.5f;            /* beyond: no cell can hold a sample */
-    std::vector<std::pair<float, int>> nearv, farv;
-    for (int t = 0; t < nt; ++t) {
-        const int x0 = (t % nt1) * SC_T - n / 2, y0 = (t / nt1) * SC_T - n / 2;
-        const float dx = x0 > 0 ? (float)x0 : (x0 + SC_T - 1 < 0 ? (float)-(x0 + SC_T - 1) : 0.f);
-        const float dy = y0 > 0 ? (float)y0 : (y0 + SC_T - 1 < 0 ? (float)-(y0 + SC_T - 1) : 0.f);
-        const float d2 = dx * dx + dy * dy;
-        const int packed = ((t / nt1) << 16) | (t % nt1);
-        const int2 w = hw[t];
-        if (w.x != CELL_ALL_SPOKES && w.y < w.x) {             /* no cell of the tile is ever tapped: only zeros to store */
-            if (d2 <= rz * rz) farv.push_back(std::make_pair(d2, packed));
-            else sp.ntiles_empty += 1;
-            continue;
-        }
-        const float frac = w.x == CELL_ALL_SPOKES ? 1.f : (float)(w.y - w.x + 1) / (float)nbins;
-        if (frac >= near_frac) nearv.push_back(std::make_pair(d2, packed)); else farv.push_back(std::make_pair(d2, packed));
+    const float near_frac_short = getenv("TRON_SCATTER_NEAR_SHORT") ? (float)atof(getenv("TRON_SCATTER_NEAR_SHORT")) : 0.1f;
+    TRON_CUDA(cudaStreamSynchronize(s));
+    rc = build_scatter_schedule(&sp.sched, &sp.n_near, &sp.n_far, &sp.ntiles_empty, sp.tile_win, n, nbins, W, near_frac);
+    if (rc) return rc;
+    int nempty = 0;
+    rc = build_scatter_schedule(&sp.sched_short, &sp.n_near_short, &sp.n_far_short, &nempty, sp.tile_win, n, nbins, W, near_frac_short);
+    if (rc) return rc;
+    sp.chain_short = sp.chain; sp.chain_near_short = sp.chain_near;
+    if (sp.chain > 1) {
+        const int cs = getenv("TRON_SCATTER_CHAIN_SHORT") ? atoi(getenv("TRON_SCATTER_CHAIN_SHORT")) : 16;
+        const int cn = getenv("TRON_SCATTER_CHAIN_NEAR_SHORT") ? atoi(getenv("TRON_SCATTER_CHAIN_NEAR_SHORT")) : 8;
+        sp.chain_short = cs > 0 && cs < sp.chain ? cs : sp.chain;
+        while (sp.chain % sp.chain_short) --sp.chain_short;          /* launches start on long-chain boundaries */
+        sp.chain_near_short = cn > 0 && cn < sp.chain_short ? cn : sp.chain_short;
+        while (sp.chain_short % sp.chain_near_short) --sp.chain_near_short;
     }
-    std::sort(nearv.begin(), nearv.end());
-    std::sort(farv.begin(), farv.end());
-    std::vector<int> order;
-    for (size_t i = 0; i < nearv.size(); ++i) order.push_back(nearv[i].second);
-    for (size_t i = 0; i < farv.size(); ++i) order.push_back(farv[i].second);
-    /* tiles beyond the last annulus come last: they are only visited when every cell must be stored */
-    for (int t = 0; t < nt; ++t) {
-        const int x0 = (t % nt1) * SC_T - n / 2, y0 = (t / nt1) * SC_T - n / 2;
-        const float dx = x0 > 0 ? (float)x0 : (x0 + SC_T - 1 < 0 ? (float)-(x0 + SC_T - 1) : 0.f);
-        const float dy = y0 > 0 ? (float)y0 : (y0 + SC_T - 1 < 0 ? (float)-(y0 + SC_T - 1) : 0.f);
-        const int2 w = hw[t];
-        if (w.x != CELL_ALL_SPOKES && w.y < w.x && dx * dx + dy * dy > rz * rz) order.push_back(((t / nt1) << 16) | (t % nt1));
-    }
-    sp.n_near = (int)nearv.size(); sp.n_far = (int)farv.size();
-    TRON_CUDA(cudaMalloc(&sp.sched, order.size() * sizeof(int)));
-    TRON_CUDA(cudaMemcpy(sp.sched, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    sp.short_below = getenv("TRON_SCATTER_SHORT_BELOW") ? atoi(getenv("TRON_SCATTER_SHORT_BELOW")) : 160;
     sp.ready = 1;
     return 0;
 }
@@ -522,7 +538,11 @@ template <int CH, bool HALF>
 static int launch_scatter_t(const GridLaunch &g, cudaStream_t s)
 {
     using P = ScPlane<CH>;
-    const ScatterPlan &sp = *g.scat;
+    ScatterPlan sp = *g.scat;
+    if (g.nslices < sp.short_below) {                        /* too few (tile, chain) tasks for the long schedule */
+        sp.sched = sp.sched_short; sp.n_near = sp.n_near_short; sp.n_far = sp.n_far_short;
+        sp.chain = sp.chain_short; sp.chain_near = sp.chain_near_short;
+    }
     const unsigned samp = CH * (HALF ? 4u : 8u);
     /* longest run a spoke can have inside a tile's box: its diagonal (+ margins) */
     const float bw = (float)(SC_T - 1) + 2.f * g.kb.W + 0.2f;

@@ -51,6 +51,10 @@ struct ScatterPlan {
     int chain = 1, chain_near = 1;                           /* slices per chain for far / near tiles */
     int n_near = 0, n_far = 0, ntiles_empty = 0;
     int ready = 0;
+    /* the schedule above serves long launches; launches of fewer than `short_below` slices have too few
+     * (tile, chain) tasks to fill the GPU and take this one: shorter chains, more tiles on the split path */
+    int *sched_short = nullptr;
+    int chain_short = 1, chain_near_short = 1, n_near_short = 0, n_far_short = 0, short_below = 0;
 };
 
 struct GridLaunch {               /* everything the gridding kernel needs */
