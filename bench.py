@@ -669,6 +669,24 @@ def run_ours(args):
                                   "unit": "samples/s", "runs_ms": cold, "plan_create_ms_first": plan_create_ms,
                                   "how": "legacy recon_radial2d(h_out, h_in): tron_plan_create + tron_recon_host + "
                                          "tron_plan_destroy per call, CUDA context already up (as in the reference arm)"}
+        if world == 1:
+            # the same job with fp16 storage at the boundary (north-star item 4): complex-half samples in,
+            # complex-half images out, f32 arithmetic -- half the PCIe bytes in both directions
+            try:
+                p16 = t.Plan(t.make_config(dims, device=local, half_in=True, half_out=True, **flags))
+                h_in16 = torch.empty(in_elems * 2, dtype=torch.float16, pin_memory=True)
+                h_in16.copy_(h_in)
+                h_out16 = torch.zeros(out_elems * 2, dtype=torch.float16, pin_memory=True)
+                ms16 = time_wall(torch, lambda: p16.recon_host_ptr(h_out16.data_ptr(), h_in16.data_ptr()), args.steps, 2)
+                extras["e2e_fp16_storage"] = {
+                    "value": nsamp / (ms16 * 1e-3), "unit": "samples/s", "ms_per_step": ms16,
+                    "h2d_bytes_per_step": in_elems * 4, "d2h_bytes_per_step": out_elems * 4,
+                    "rel_l2_vs_f32_path": rel_l2_t(h_out16.float(), h_out), "tolerance": 2e-3,
+                    "how": "tron_recon_host with half_in + half_out (complex-half RA payloads), f32 arithmetic"}
+                p16.close()
+                del h_in16, h_out16
+            except Exception as e:
+                extras["e2e_fp16_storage"] = {"error": "%s: %s" % (type(e).__name__, e)}
         plan.close(); plan = None
         del d_in, d_out, h_in, h_out
         torch.cuda.empty_cache()

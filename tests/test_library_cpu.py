@@ -258,3 +258,42 @@ def test_float_to_half_matches_oracle_and_ieee(lib, oracle):
         b = struct.unpack("<Q", struct.pack("<d", v))[0]
         with np.errstate(over="ignore"):
             assert lib.tron_doublebits_to_halfbits(b) == int(np.float64(v).astype(np.float16).view(np.uint16))
+
+
+def test_ra_reader_rejects_crafted_headers(lib, tmp_path):
+    """A file cannot claim pinned storage (the in-memory RA_FLAG_PINNED_DATA bit would send ra_free to
+    cudaFreeHost with a malloc'ed pointer), and its size field must equal prod(dims) * elbyte."""
+    import tron_b200 as t
+    f = str(tmp_path / "ok.ra")
+    a = np.arange(24, dtype=np.float32)
+    t.ra_write(f, a, dims=[4, 6], eltype=3)
+    raw = bytearray(open(f, "rb").read())
+    pinned = bytearray(raw)
+    struct.pack_into("<Q", pinned, 8, 1 << 62)                    # flags word: the in-memory pinned bit
+    fp = str(tmp_path / "pinned.ra")
+    open(fp, "wb").write(pinned)
+    r = t.api.RaStruct()
+    assert lib.ra_read(C.byref(r), fp.encode()) == 0
+    assert r.flags & (1 << 62) == 0
+    lib.ra_free(C.byref(r))
+    wrong = bytearray(raw)
+    struct.pack_into("<Q", wrong, 32, len(a) * 4 + 4)             # size field off by one element
+    fw = str(tmp_path / "wrong.ra")
+    open(fw, "wb").write(wrong + b"\0\0\0\0")
+    with pytest.raises(t.TronError):
+        t.ra_read(fw)
+    huge = bytearray(raw)
+    struct.pack_into("<2Q", huge, 48, 1 << 40, 1 << 40)           # dims whose product wraps 64 bits with elbyte
+    fh = str(tmp_path / "huge.ra")
+    open(fh, "wb").write(huge)
+    with pytest.raises(t.TronError):
+        t.ra_read(fh)
+    with pytest.raises(t.TronError, match="2\\^60"):
+        t.geometry(t.make_config([1 << 30, 1, 1 << 30, 1 << 30, 1], adjoint=True))
+
+
+def test_build_records_the_hash_of_its_sources(lib):
+    """load/build use the library as is only when it was built from the sources in the tree."""
+    from tron_b200 import build
+    assert os.path.isfile(build.HASHFILE)
+    assert open(build.HASHFILE).read().strip() == build.source_hash()

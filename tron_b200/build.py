@@ -38,6 +38,27 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+HASHFILE = LIB + ".srchash"
+
+
+def source_hash():
+    """sha256 over the sources the library is built from (and the build flags)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(sources()):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _recorded_hash():
+    try:
+        return open(HASHFILE).read().strip()
+    except OSError:
+        return None
+
+
 def sources():
     out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     out += [os.path.join(HERE, "..", "include", f) for f in ("tron.h", "ra.h", "float16.h")]
@@ -50,6 +71,18 @@ def build(force=False, verbose=False, check_stale=False):
     staleness check there would rebuild -- concurrently on all ranks).  `force` / `check_stale`
     (the `python -m tron_b200.build` entry) rebuild when sources are newer."""
     if os.path.exists(LIB) and os.path.exists(EXE) and not force and not check_stale:
+        # An existing library is used as is -- unless it was built from OTHER sources than the ones in the tree
+        # (edited csrc/*.cu and a test run on the previous binary would report green for code that never ran).
+        # The check is a content hash written next to the library, not mtimes: the snapshot on the GPU box has
+        # arbitrary mtimes and every rank of a torchrun launch comes through here.  A rebuild is serialised by a
+        # file lock.
+        if shutil.which("nvcc") is None or _recorded_hash() == source_hash():
+            return LIB
+        import fcntl
+        with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if _recorded_hash() != source_hash():
+                return build(force=True, verbose=verbose)
         return LIB
     if shutil.which("nvcc") is None:
         if os.path.exists(LIB):
@@ -85,6 +118,8 @@ def build(force=False, verbose=False, check_stale=False):
     _run(["nvcc"] + NVCC_FLAGS + [os.path.join(CSRC, "tron_main.cu"), "-o", EXE,
                                   "-L" + LIBDIR, "-ltron_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib"])
     shutil.rmtree(objdir, ignore_errors=True)
+    with open(HASHFILE, "w") as fh:
+        fh.write(source_hash() + "\n")
     if verbose:
         print("\n".join(log))
     return LIB

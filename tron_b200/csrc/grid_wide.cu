@@ -32,7 +32,7 @@ namespace tronb {
 struct __align__(16) WideList {
     float4 wa[WCAP];                  /* weights of cells (0..3, row 0) */
     float4 wb[WCAP];                  /* weights of cells (0..3, row 1) */
-    int off[WCAP];                    /* sample offset in elements from the group's channel base */
+    unsigned off[WCAP];               /* sample offset in elements from the group's channel base (launch checks it fits 32 bits) */
     int mask[WCAP];                   /* slices of the group whose window holds the spoke */
 };
 
@@ -87,7 +87,7 @@ __device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], WideLis
         float2 x[DEPTH][NCHUNK];
 #pragma unroll
         for (int d = 0; d < DEPTH; ++d) {
-            const int off = L.off[e0 + d * EPI + sub];
+            const unsigned off = L.off[e0 + d * EPI + sub];
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c)
                 x[d][c] = load_chan<HALF>(samples, (size_t)off + min(c * 32 + ch, nvalid - 1));
@@ -266,7 +266,7 @@ grid_wide_kernel(const GridLaunch g)
                         const int slot = cnt + __popc(hit & ((1u << lane) - 1u));
                         L.wa[slot] = make_float4(w8[0], w8[1], w8[2], w8[3]);
                         L.wb[slot] = make_float4(w8[4], w8[5], w8[6], w8[7]);
-                        L.off[slot] = ((pmo & 0xffffff) * g.nro + g.nro / 2 + ridx) * g.nc_total;
+                        L.off[slot] = (unsigned)(((pmo & 0xffffff) * g.nro + g.nro / 2 + ridx)) * (unsigned)g.nc_total;
                         L.mask[slot] = pmo >> 24;
                     }
                     cnt += __popc(hit);
@@ -333,6 +333,9 @@ bool grid_wide_applicable(const GridLaunch &g)
     if (g.nch < 32 || g.nch % 16 != 0) return false;
     if (g.n % 4 != 0) return false;
     if (g.gs != 1 && g.gs != 4) return false;
+    /* sample offsets inside a table's window are 32-bit element counts: (window spokes * nro) * nc must fit */
+    if ((unsigned long long)g.npe * (unsigned long long)g.nro * (unsigned long long)g.nc_total >= (1ull << 32)) return false;
+    if ((unsigned long long)g.npe * (unsigned long long)g.nro >= (1ull << 31)) return false;
     return true;
 }
 

@@ -21,6 +21,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <vector>
 
 namespace tronb {
@@ -65,6 +66,11 @@ extern "C" int tron_geometry_compute(const tron_config *c, tron_geometry *g)
     if (c->koosh) { set_error("-3 (koosh ball) has no kernels in the reference either"); return TRON_EUNSUPPORTED; }
     if (!(c->gridos > 0.f) || !(c->kernwidth > 0.f) || !(c->data_undersamp > 0.f)) { set_error("gridos, kernwidth and data_undersamp must be positive"); return TRON_EINVAL; }
     for (int i = 0; i < 5; ++i) if (c->dims[i] == 0 || c->dims[i] > 0x7fffffffULL) { set_error("dims[%d] = %llu out of range", i, (unsigned long long)c->dims[i]); return TRON_EINVAL; }
+    {   /* five 31-bit factors can wrap 64 bits: the payload-size checks downstream rely on these products */
+        unsigned __int128 prod = 1;
+        for (int i = 0; i < 5; ++i) prod *= c->dims[i];
+        if (prod > ((unsigned __int128)1 << 60)) { set_error("the array described by dims holds more than 2^60 elements"); return TRON_EINVAL; }
+    }
     g->nc = (int)c->dims[0]; g->nt = (int)c->dims[1];
     g->out_dims[0] = 1;                                    /* tron.cu:899 */
     int slide = c->prof_slide;
@@ -182,6 +188,15 @@ static int pick_batch(const tron_plan *p)
     return (int)b;
 }
 
+/* the FFT, degridding and combine launches put slices x channels (or slices) into gridDim.y (<= 65535) */
+static int clamp_batch_to_launch_limits(const tron_plan *p, int batch)
+{
+    const int per = p->nch > 0 ? p->nch : 1;
+    const int lim = 65535 / per;
+    if (batch > lim) batch = lim;
+    return batch < 1 ? 1 : batch;
+}
+
 extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
 {
     *out = nullptr;
@@ -214,6 +229,16 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
     p->in_bytes = g.shard_in_elems * p->in_elem_bytes;
     p->out_bytes = g.shard_out_elems * p->out_elem_bytes;
 
+    /* TRON_PLAN_TRACE: wall-clock milliseconds of each stage of plan creation on stderr */
+    const bool ptrace = getenv("TRON_PLAN_TRACE") != nullptr;
+    struct timespec pt0; clock_gettime(CLOCK_MONOTONIC, &pt0);
+    auto pmark = [&](const char *what) {
+        if (!ptrace) return;
+        cudaDeviceSynchronize();
+        struct timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "tron plan trace: %-28s %8.3f ms\n", what, (t1.tv_sec - pt0.tv_sec) * 1e3 + (t1.tv_nsec - pt0.tv_nsec) * 1e-6);
+        pt0 = t1;
+    };
 #define PLAN_TRY(call) do { int rc__ = (call); if (rc__) { plan_release(p); return rc__; } } while (0)
 #define PLAN_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
         int rc__ = cuda_fail(e__, #call, __FILE__, __LINE__); plan_release(p); return rc__; } } while (0)
@@ -235,6 +260,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_user, cudaEventDisableTiming));
     }
     for (int i = 0; i < 4; ++i) PLAN_CUDA(cudaEventCreate(&p->ev_t[i]));
+    pmark("streams and events");
 
     const int n = g.nxos;
     if (cfg->adjoint) {
@@ -253,7 +279,9 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         PLAN_TRY(launch_build_tables(p->tabs, g.npe1work, g.npe1work, 1, 0, cfg->skip_angles, cfg->golden_angle, 0,
                                      g.npe1work, 0, 1, 1, n, cfg->kernwidth, p->stream));
     }
+    pmark("spoke and cell tables");
     PLAN_TRY(fft_plan_init(p->fft, n, g.nx));
+    pmark("fft plan");
     if (cfg->adjoint && p->fft.pow2 && !getenv("TRON_NO_ZERO_SKIP")) {
         /* a cell receives samples only if ceil(R - W) <= nxos/2 - 1 (tron.cu:498-502): beyond
          * R = nxos/2 - 1 + W (+0.5 of margin for the float hypot) the grid is identically zero; the
@@ -279,6 +307,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
             p->heavy_big = (double)n * n * ((per_launch + gsz - 1) / gsz) >= 2.0e6;
             if (getenv("TRON_HEAVY_BIG")) p->heavy_big = atoi(getenv("TRON_HEAVY_BIG")) != 0;
         }
+        pmark("tile orders, heavy cells");
         PLAN_TRY(build_tile_windows(&p->tile_win8, p->tabs.cells, n, p->tabs.nbins, 8, 4, p->stream));
         /* sliding windows: all but the first slice group of a chain are gridded from what enters and leaves
          * the window (grid_tile.cu); worth it when that is clearly fewer spokes than a group's union window */
@@ -294,6 +323,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
                                             g.prof_slide, gsz, p->nslices, p->stream));
             }
         }
+        pmark("tile windows, delta tables");
         /* tiles accumulated in shared memory, sample driven (grid_scatter.cu): the default where it applies */
         {
             const bool fits = p->kb.fast && cfg->kernwidth == 2.0f && g.nro == g.nxos && p->nch == g.nc
@@ -307,15 +337,21 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         PLAN_TRY(build_tile_schedule(&p->tile_sched8, &p->n_near8, n, 8,
                                      getenv("TRON_TILE_NEAR") ? (float)atof(getenv("TRON_TILE_NEAR")) : 32.f));
     }
+    pmark("scatter plan, tile schedule");
     PLAN_CUDA(cudaMalloc(&p->deapod_adj, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_CUDA(cudaMalloc(&p->deapod_fwd, (size_t)g.nx * g.nx * sizeof(float)));
     PLAN_TRY(launch_deapod_tables(p->deapod_adj, p->deapod_fwd, g.nx, n, cfg->kernwidth, cfg->gridos, p->stream));
 
-    p->batch = cfg->adjoint ? pick_batch(p) : 1;
+    pmark("deapodisation tables");
+    p->batch = cfg->adjoint ? clamp_batch_to_launch_limits(p, pick_batch(p)) : 1;
+    if (p->nch > 65535) { set_error("nc = %d channels exceed the launch limits (65535)", p->nch); plan_release(p); return TRON_EUNSUPPORTED; }
+    if (cfg->kernwidth > 7.5f) { set_error("kernel half-width %.2f > 7.5: outside the kernels' tap windows", cfg->kernwidth); plan_release(p); return TRON_EUNSUPPORTED; }
+    if (cfg->adjoint && cfg->coil_combine == 1 && g.nc > 128) { set_error("the Walsh combine supports at most 128 channels (nc = %d)", g.nc); plan_release(p); return TRON_EUNSUPPORTED; }
     if (cfg->adjoint && p->tabs.gs > 1) {                /* launches start on group (chain) boundaries */
         int q = p->tabs.gs * (p->chain > 0 ? p->chain : 1);
         if (p->scat.ready && p->scat.chain > q) q = p->scat.chain;
         p->batch = ((p->batch + q - 1) / q) * q;
+        while (p->batch > q && (long long)p->batch * p->nch > 65535) p->batch -= q;
     }
     p->stage_timing = getenv("TRON_STAGE_TIMING") != nullptr;
     if (cfg->adjoint && getenv("TRON_GRID_DEBUG")) {
@@ -350,6 +386,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         }
     }
     PLAN_CUDA(cudaStreamSynchronize(p->stream));
+    pmark("work buffers");
 #undef PLAN_TRY
 #undef PLAN_CUDA
     *out = p;

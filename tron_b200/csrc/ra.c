@@ -56,7 +56,8 @@ static int read_header_fd(int fd, ra_t *a)
     int rc = read_fully(fd, h, sizeof h);
     if (rc) return rc;
     if (h[0] != RA_MAGIC_NUMBER) { fprintf(stderr, "Invalid RA file.\n"); return -EINVAL; }
-    a->flags = h[1]; a->eltype = h[2]; a->elbyte = h[3]; a->size = h[4]; a->ndims = h[5];
+    a->flags = h[1] & ~(uint64_t)RA_FLAG_PINNED_DATA;      /* in-memory only: a file cannot claim pinned storage */
+    a->eltype = h[2]; a->elbyte = h[3]; a->size = h[4]; a->ndims = h[5];
     if (a->flags & ~(uint64_t)(RA_FLAG_BIG_ENDIAN | RA_FLAG_COMPRESSED))
         fprintf(stderr, "Warning: RA file carries flags this reader does not know (0x%llx).\n",
                 (unsigned long long)a->flags);
@@ -64,6 +65,19 @@ static int read_header_fd(int fd, ra_t *a)
     a->dims = (uint64_t *)malloc(sizeof(uint64_t) * a->ndims);
     if (!a->dims) return -ENOMEM;
     rc = read_fully(fd, a->dims, sizeof(uint64_t) * a->ndims);
+    if (!rc && !(a->flags & RA_FLAG_COMPRESSED)) {
+        /* size must be prod(dims) * elbyte (ra.cu:141-147 writes it that way); the product is overflow checked */
+        uint64_t ne = 1;
+        int bad = a->elbyte == 0;
+        for (uint64_t i = 0; i < a->ndims && !bad; ++i) {
+            if (a->dims[i] != 0 && ne > UINT64_MAX / a->dims[i]) bad = 1; else ne *= a->dims[i];
+        }
+        if (!bad && ne != 0 && a->elbyte > UINT64_MAX / ne) bad = 1;
+        if (bad || ne * a->elbyte != a->size) {
+            fprintf(stderr, "Invalid RA file: size field %llu does not match its dims and element size.\n", (unsigned long long)a->size);
+            rc = -EINVAL;
+        }
+    }
     if (rc) { free(a->dims); a->dims = NULL; }
     return rc;
 }

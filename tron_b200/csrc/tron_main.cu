@@ -100,6 +100,7 @@ int main(int argc, char *argv[])
     VPRINT("Reading %s\n", infile);
     ra_t ra_in;
     if (ra_read_pinned(&ra_in, infile)) return 74;                      /* EX_IOERR, as ra.cu:56-84 */
+    if (ra_in.flags & (RA_FLAG_BIG_ENDIAN | RA_FLAG_COMPRESSED)) { fprintf(stderr, "tron: big-endian or compressed RA payloads are not supported (flags 0x%llx)\n", (unsigned long long)ra_in.flags); return 65; }
     if (ra_in.ndims != 5) { fprintf(stderr, "tron: input must be 5-D [nc, nt, d2, d3, d4], got %llu dims\n", (unsigned long long)ra_in.ndims); return 65; }
     if (ra_in.eltype == RA_TYPE_COMPLEX && ra_in.elbyte == 4) cfg.half_in = 1;
     else if (!(ra_in.eltype == RA_TYPE_COMPLEX && ra_in.elbyte == 8)) {
