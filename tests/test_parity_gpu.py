@@ -315,6 +315,11 @@ def test_tile_kernel_matches_l1_gather(lib, monkeypatch, nchan, half, flags, env
     (4, False, 128, dict(golden=False, prof_slide=40, undersamp=0.4), {}),                                    # linear angles: one shared table
     (6, False, 256, dict(golden=True), {}),                                                                   # one slice, 256^2
     (6, True, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {}),                                      # fp16 storage: 24-byte samples
+    (16, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {}),                                    # 16 coils: half-warps share a sample, 16 x 8 tiles
+    (16, False, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_SHORT_BELOW": "0"}),
+    (16, False, 96, dict(golden=True, undersamp=0.4, prof_slide=5, skip_angles=3), {"TRON_SCATTER_NEAR_SHORT": "0"}),
+    (16, True, 128, dict(golden=True, undersamp=0.25, prof_slide=3), {"TRON_SCATTER_CHAIN": "1"}),            # fp16 storage, every slice in full
+    (16, False, 64, dict(golden=False), {}),                                                                  # one slice, linear angles
     (2, True, 128, dict(golden=True, undersamp=0.3, prof_slide=5), {"TRON_SCATTER_CAP": "512"}),
 ])
 def test_scatter_kernel_matches_l1_gather(lib, monkeypatch, nchan, half, nro, flags, env):

@@ -19,7 +19,7 @@ EXE = os.path.join(BINDIR, "tron")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "--use_fast_math", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-Xcompiler", "-fvisibility=default", "-w"] + ARCH
+              "-Xcompiler", "-fvisibility=default", "-w"] + ARCH + os.environ.get("TRON_NVCC_EXTRA", "").split()
 CU_SOURCES = ["plan.cu", "grid.cu", "grid_tile.cu", "grid_scatter.cu", "grid_wide.cu", "degrid.cu", "degrid_wide.cu", "fft.cu", "combine.cu", "cgnr.cu", "legacy.cu", "comm.cu"]
 HOST_SOURCES = ["ra.c", "float16.cpp"]
 

@@ -45,17 +45,36 @@ namespace tronb {
 #define SC_T 16                 /* tile edge (cells) */
 #define SC_SLOTS 32             /* spokes per staging round (one per lane) */
 #define SC_WARPS 4
+#ifndef SC_UNROLL
+#define SC_UNROLL 2             /* steps per trip of the sample loop */
+#endif
 #define SC_HDR 2112             /* bytes of per-warp bookkeeping ahead of the tile: barriers, round info, descriptors, annuli */
 
-/* tile rows are padded so that the 16-byte accesses of a quarter warp (2 rows x 4 cells) fall into 8 different
- * bank groups whatever the sample's position: row stride = 4 (mod 8) sixteen-byte units, 1 (mod 8) for nc = 4 */
+/* Tile geometry and shared-memory layout per channel count.
+ *  nc <= 6:  16 x 16 tiles, a lane holds all nc channels of its cell (16-byte units back to back); rows are padded so
+ *            that the 16-byte accesses of a quarter warp (2 rows x 4 cells) fall into 8 different bank groups whatever
+ *            the sample's position: row stride = 4 (mod 8) units, 1 (mod 8) for nc = 4.
+ *  nc = 16:  16 x 8 tiles; BOTH half-warps take the same sample, half h holds channels 8h .. 8h+7 of its cell
+ *            (SHARE).  A cell is 128 bytes = all 8 bank groups, so its units are swizzled:
+ *            physical unit = logical ^ (cx & 7) ^ ((cy & 1) << 2) -- a quarter warp's 2 x 4 cells then touch 8
+ *            different groups for every logical unit. */
 template <int CH> struct ScPlane {
+    static constexpr bool SHARE = CH > 8;
+    static constexpr int TH = SHARE ? 8 : 16;               /* tile height (rows) */
+    static constexpr int LCH = SHARE ? CH / 2 : CH;         /* channels per lane */
     static constexpr int CELL = CH * 8;
     static constexpr int UNITS = SC_T * CH / 2;
     static constexpr int WANT = CH == 4 ? 1 : 4;
-    static constexpr int PAD = (WANT + 8 - UNITS % 8) % 8;
+    static constexpr int PAD = SHARE ? 0 : (WANT + 8 - UNITS % 8) % 8;
     static constexpr int ROW = (UNITS + PAD) * 16;
-    static constexpr int BYTES = ROW * SC_T;
+    static constexpr int BYTES = ROW * TH;
+    /* byte offset inside the tile of 16-byte unit `u` (0 .. LCH/2 - 1) of the channels half `hf` holds in cell (cx, cy) */
+    __device__ static __forceinline__ unsigned unit(int cx, int cy, int hf, int u)
+    {
+        if (!SHARE) return (unsigned)(cy * ROW + cx * CELL + 16 * u);
+        const int sw = (cx & 7) ^ ((cy & 1) << 2);
+        return (unsigned)(cy * ROW + cx * CELL + 16 * (((hf * (LCH / 2) + u) ^ sw) & 7));
+    }
 };
 
 /* ---------------------------------------------------------------------- */
@@ -131,18 +150,18 @@ void scatter_plan_free(ScatterPlan &sp)
 /* tile schedule: nearest DC first; tiles whose angular window holds at least `near_frac` of all spokes are
  * "near": one block (4 warps splitting the spokes) per tile and short chain.  order = near | far | empty. */
 static int build_scatter_schedule(int **d_sched, int *n_near, int *n_far, int *n_empty, const int2 *d_tile_win, int n,
-                                  int nbins, float W, float near_frac)
+                                  int nbins, float W, float near_frac, int th)
 {
-    const int nt1 = (n + SC_T - 1) / SC_T, nt = nt1 * nt1;
+    const int nt1 = (n + SC_T - 1) / SC_T, nty = (n + th - 1) / th, nt = nt1 * nty;
     std::vector<int2> hw(nt);
     TRON_CUDA(cudaMemcpy(hw.data(), d_tile_win, nt * sizeof(int2), cudaMemcpyDeviceToHost));
     const float rz = (float)(n / 2 - 1) + W + 0.5f;            /* beyond: no cell can hold a sample */
     std::vector<std::pair<float, int>> nearv, farv;
     std::vector<int> empty;
     for (int t = 0; t < nt; ++t) {
-        const int x0 = (t % nt1) * SC_T - n / 2, y0 = (t / nt1) * SC_T - n / 2;
+        const int x0 = (t % nt1) * SC_T - n / 2, y0 = (t / nt1) * th - n / 2;
         const float dx = x0 > 0 ? (float)x0 : (x0 + SC_T - 1 < 0 ? (float)-(x0 + SC_T - 1) : 0.f);
-        const float dy = y0 > 0 ? (float)y0 : (y0 + SC_T - 1 < 0 ? (float)-(y0 + SC_T - 1) : 0.f);
+        const float dy = y0 > 0 ? (float)y0 : (y0 + th - 1 < 0 ? (float)-(y0 + th - 1) : 0.f);
         const float d2 = dx * dx + dy * dy;
         const int packed = ((t / nt1) << 16) | (t % nt1);
         const int2 w = hw[t];
@@ -168,10 +187,11 @@ static int build_scatter_schedule(int **d_sched, int *n_near, int *n_far, int *n
 
 /* `cells` / `nbins`: the per-cell table of the plan's spoke tables (slice independent), shared with the gather kernels */
 int scatter_plan_build(ScatterPlan &sp, const int2 *cells, int nbins, int n, int nslices, int win, int slide, int skip,
-                       int golden, float W, cudaStream_t s)
+                       int golden, float W, int nc, cudaStream_t s)
 {
     sp = ScatterPlan();
     sp.win = win;
+    sp.th = nc > 8 ? 8 : 16;                                /* ScPlane<nc>::TH */
     /* difference tables pay when a slice's difference is clearly fewer spokes than its window */
     const bool sliding = golden && nslices > 1 && 4 * slide <= win;
     sp.per_slice = golden ? 1 : 0;
@@ -190,15 +210,15 @@ int scatter_plan_build(ScatterPlan &sp, const int2 *cells, int nbins, int n, int
         if (sp.chain_near > sp.chain) sp.chain_near = sp.chain;
         while (sp.chain % sp.chain_near) --sp.chain_near;      /* near chains nest in the far ones */
     }
-    rc = build_tile_windows(&sp.tile_win, cells, n, nbins, SC_T, SC_T, s);
+    rc = build_tile_windows(&sp.tile_win, cells, n, nbins, SC_T, sp.th, s);
     if (rc) return rc;
     const float near_frac = getenv("TRON_SCATTER_NEAR") ? (float)atof(getenv("TRON_SCATTER_NEAR")) : 0.25f;
     const float near_frac_short = getenv("TRON_SCATTER_NEAR_SHORT") ? (float)atof(getenv("TRON_SCATTER_NEAR_SHORT")) : 0.1f;
     TRON_CUDA(cudaStreamSynchronize(s));
-    rc = build_scatter_schedule(&sp.sched, &sp.n_near, &sp.n_far, &sp.ntiles_empty, sp.tile_win, n, nbins, W, near_frac);
+    rc = build_scatter_schedule(&sp.sched, &sp.n_near, &sp.n_far, &sp.ntiles_empty, sp.tile_win, n, nbins, W, near_frac, sp.th);
     if (rc) return rc;
     int nempty = 0;
-    rc = build_scatter_schedule(&sp.sched_short, &sp.n_near_short, &sp.n_far_short, &nempty, sp.tile_win, n, nbins, W, near_frac_short);
+    rc = build_scatter_schedule(&sp.sched_short, &sp.n_near_short, &sp.n_far_short, &nempty, sp.tile_win, n, nbins, W, near_frac_short, sp.th);
     if (rc) return rc;
     sp.chain_short = sp.chain; sp.chain_near_short = sp.chain_near;
     if (sp.chain > 1) {
@@ -264,14 +284,15 @@ __device__ __forceinline__ void scatter_task(const GridLaunch &g, const ScatterP
     const unsigned plane = w0 + SC_HDR;
     const unsigned data0 = plane + P::BYTES;
 
-    const int x0 = (tile & 0xffff) * SC_T, y0 = (tile >> 16) * SC_T;
+    constexpr int TH = P::TH, LCH = P::LCH;
+    const int x0 = (tile & 0xffff) * SC_T, y0 = (tile >> 16) * TH;
     const int XL = x0 - n / 2, YL = y0 - n / 2;
-    const int XH = min(x0 + SC_T - 1, n - 1) - n / 2, YH = min(y0 + SC_T - 1, n - 1) - n / 2;
+    const int XH = min(x0 + SC_T - 1, n - 1) - n / 2, YH = min(y0 + TH - 1, n - 1) - n / 2;
     const int nt1 = (n + SC_T - 1) / SC_T;
     const int2 tw = __ldg(sp.tile_win + (size_t)(tile >> 16) * nt1 + (tile & 0xffff));
 
     /* annuli of the tile's cells (tron.cu:498-502), slice independent */
-    for (int i = lane; i < SC_T * SC_T; i += 32) {
+    for (int i = lane; i < SC_T * TH; i += 32) {
         const int x = x0 + (i & 15), y = y0 + (i >> 4);
         unsigned a = 1u;                                   /* Rlo = 1 > Rhi = 0: never tapped */
         if (x < n && y < n) a = (unsigned)__ldg(&g.cells[(size_t)y * n + x].x);
@@ -384,19 +405,20 @@ __device__ __forceinline__ void scatter_task(const GridLaunch &g, const ScatterP
             if (len == 0) continue;
             const int ra = (pk & 0xfff) - 2048;
             const int sgn = pk & (int)0x80000000;
-            /* the two half-warps take samples >= 6 readout steps apart (disjoint supports); short runs: one half */
-            const bool two = len >= 12;
+            /* the two half-warps take samples >= 6 readout steps apart (disjoint supports); short runs: one half.
+             * SHARE (nc = 16): both halves take the same sample, each its own eight channels */
+            const bool two = !P::SHARE && len >= 12;
             const int h = two ? (len + 1) >> 1 : len;
             int r = ra + ((hf && two) ? h : 0);
-            const int mine = hf ? (two ? len - h : 0) : h;
+            const int mine = P::SHARE ? len : (hf ? (two ? len - h : 0) : h);
             /* one step = one sample per half-warp; branch free (dead lanes compute along and skip the store), two
              * steps per trip so that the second's index arithmetic and weight overlap the first's shared-memory
              * round trip */
             const int rsafe = ra;                           /* a staged sample for lanes without one of their own */
 #pragma unroll 1
-            for (int i = 0; i < h; i += 2, r += 2) {
+            for (int i = 0; i < h; i += SC_UNROLL, r += SC_UNROLL) {
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < SC_UNROLL; ++u) {
                     const bool live = i + u < mine;
                     const int re = live ? r + u : rsafe;
                     const float rf = (float)re;
@@ -407,8 +429,8 @@ __device__ __forceinline__ void scatter_task(const GridLaunch &g, const ScatterP
                     if (lx == 3 && !(fabsf(dx) < Wk)) { Xf -= 4.f; dx = fma_ftz(ct, rf, -Xf); }
                     if (ly == 3 && !(fabsf(dy) < Wk)) { Yf -= 4.f; dy = fma_ftz(st, rf, -Yf); }
                     const int cxl = (int)Xf - tX0, cyl = (int)Yf - tY0;
-                    bool ok = live && fabsf(dx) < Wk && fabsf(dy) < Wk && (unsigned)cxl < (unsigned)SC_T && (unsigned)cyl < (unsigned)SC_T;
-                    const int cxc = cxl & (SC_T - 1), cyc = cyl & (SC_T - 1);
+                    bool ok = live && fabsf(dx) < Wk && fabsf(dy) < Wk && (unsigned)cxl < (unsigned)SC_T && (unsigned)cyl < (unsigned)TH;
+                    const int cxc = cxl & (SC_T - 1), cyc = cyl & (TH - 1);
                     const unsigned ann = lds_u1(ann0 + 4u * (unsigned)(cyc * SC_T + cxc));
                     const int ar = abs(re);
                     ok = ok && ar >= (int)(ann & 0xffffu) && ar <= (int)(ann >> 16);   /* annulus, tron.cu:501-502,512,521 */
@@ -416,16 +438,16 @@ __device__ __forceinline__ void scatter_task(const GridLaunch &g, const ScatterP
                     const float sdc = fmaf(sdc_as, fabsf(rf), sdc_bs);       /* tron.cu:412, times the output scale */
                     w *= (re == 0) ? sdc + sdc : sdc;                        /* both of the reference's loops visit r = 0 */
                     w = __int_as_float(__float_as_int(w) ^ sgn);             /* leaving spoke: subtract */
-                    const unsigned sa = (unsigned)(a0 + re * (int)SAMP);
-                    const unsigned ca = plane + (unsigned)cyc * (unsigned)P::ROW + (unsigned)cxc * (unsigned)P::CELL;
-                    float2 v[CH];
-                    lds_sample<CH, HALF>(v, sa);
+                    const unsigned sa = (unsigned)(a0 + re * (int)SAMP) + (P::SHARE ? (unsigned)hf * (unsigned)(LCH * (HALF ? 4 : 8)) : 0u);
+                    float2 v[LCH];
+                    lds_sample<LCH, HALF>(v, sa);
 #pragma unroll
-                    for (int c = 0; c < CH / 2; ++c) {
-                        float4 q = lds_f4(ca + 16u * (unsigned)c);
+                    for (int c = 0; c < LCH / 2; ++c) {
+                        const unsigned ca = plane + P::unit(cxc, cyc, hf, c);
+                        float4 q = lds_f4(ca);
                         float2 q0 = make_float2(q.x, q.y), q1 = make_float2(q.z, q.w);
                         ffma2(q0, w, v[2 * c]); ffma2(q1, w, v[2 * c + 1]);
-                        sts_f4_if(ca + 16u * (unsigned)c, make_float4(q0.x, q0.y, q1.x, q1.y), ok);
+                        sts_f4_if(ca, make_float4(q0.x, q0.y, q1.x, q1.y), ok);
                     }
                     /* (no barrier between steps: the warp is converged here, its shared-memory instructions are
                      * volatile and execute in program order, so the next step's loads see this step's stores) */
@@ -443,20 +465,19 @@ __device__ __forceinline__ void scatter_task(const GridLaunch &g, const ScatterP
                 const int cy0 = lane >> 4;
                 const size_t pstride = plane_sz * sizeof(float2), rowstep = (size_t)2 * n * sizeof(float2);
                 char *obase = (char *)(g.grid + (size_t)zl * g.nch * plane_sz + (size_t)(y0 + cy0) * n + x);
-                const unsigned ca0 = plane + (unsigned)cy0 * (unsigned)P::ROW + (unsigned)cx * (unsigned)P::CELL;
-                /* which of this lane's 8 rows are stored (tile inside the grid and the last annulus: all of them) */
+                /* which of this lane's rows are stored (tile inside the grid and the last annulus: all of them) */
                 unsigned rows = 0;
 #pragma unroll
-                for (int k = 0; k < SC_T / 2; ++k) {
+                for (int k = 0; k < TH / 2; ++k) {
                     const int y = y0 + cy0 + 2 * k, Y = y - n / 2;
                     if (x < n && y < n && (store_all || X * X + Y * Y <= g.zero_r2)) rows |= 1u << k;
                 }
 #pragma unroll
-                for (int c = 0; c < CH / 2; ++c) {
+                for (int c = 0; c < CH / 2; ++c) {          /* c-th pair of coil planes */
                     char *oa = obase + (size_t)(2 * c) * pstride, *ob = oa + pstride;
 #pragma unroll 4
-                    for (int k = 0; k < SC_T / 2; ++k) {
-                        const float4 q = lds_f4(ca0 + (unsigned)(2 * k * P::ROW + 16 * c));
+                    for (int k = 0; k < TH / 2; ++k) {
+                        const float4 q = lds_f4(plane + P::unit(cx, cy0 + 2 * k, c / (LCH / 2), c % (LCH / 2)));
                         if (rows & (1u << k)) { __stcs((float2 *)oa, make_float2(q.x, q.y)); __stcs((float2 *)ob, make_float2(q.z, q.w)); }
                         oa += rowstep; ob += rowstep;
                     }
@@ -465,19 +486,19 @@ __device__ __forceinline__ void scatter_task(const GridLaunch &g, const ScatterP
                 bar_sync_block(1, SC_WARPS * 32);           /* every warp's partial tile of this slice is complete */
                 const int t = threadIdx.x;
 #pragma unroll 1
-                for (int k = 0; k < SC_T / 8; ++k) {
+                for (int k = 0; k < TH / 8; ++k) {
                     const int cy = 8 * k + (t >> 4), cx = t & 15;
                     const int x = x0 + cx, y = y0 + cy;
                     const int X = x - n / 2, Y = y - n / 2;
                     const bool st_ok = x < n && y < n && (store_all || X * X + Y * Y <= g.zero_r2);
-                    const unsigned off = (unsigned)SC_HDR + (unsigned)cy * (unsigned)P::ROW + (unsigned)cx * (unsigned)P::CELL;
                     float2 *o = g.grid + (size_t)zl * g.nch * plane_sz + (size_t)y * n + x;
 #pragma unroll
                     for (int c = 0; c < CH / 2; ++c) {
-                        float4 q = lds_f4(smem_u32(smem_raw) + off + 16u * (unsigned)c);
+                        const unsigned off = (unsigned)SC_HDR + P::unit(cx, cy, c / (LCH / 2), c % (LCH / 2));
+                        float4 q = lds_f4(smem_u32(smem_raw) + off);
 #pragma unroll
                         for (int ww = 1; ww < SC_WARPS; ++ww) {
-                            const float4 p = lds_f4(smem_u32(smem_raw) + (unsigned)ww * per_warp + off + 16u * (unsigned)c);
+                            const float4 p = lds_f4(smem_u32(smem_raw) + (unsigned)ww * per_warp + off);
                             q.x += p.x; q.y += p.y; q.z += p.z; q.w += p.w;
                         }
                         if (st_ok) { __stcs(o + (size_t)(2 * c) * plane_sz, make_float2(q.x, q.y)); __stcs(o + (size_t)(2 * c + 1) * plane_sz, make_float2(q.z, q.w)); }
@@ -528,8 +549,9 @@ bool grid_scatter_applicable(const GridLaunch &g)
     if (!g.scat || !g.scat->ready) return false;
     if (!(g.kb.fast && g.nro == g.n && g.kb.W == 2.0f)) return false;    /* 4 x 4 supports, ridx = r */
     if (g.nch != g.nc_total || g.ch0 != 0) return false;     /* whole samples are staged */
-    if (g.nch != 2 && g.nch != 4 && g.nch != 6) return false;
+    if (g.nch != 2 && g.nch != 4 && g.nch != 6 && g.nch != 16) return false;
     if (g.n % SC_T != 0 || g.n > 4096) return false;
+    if (g.scat->th != (g.nch > 8 ? 8 : 16)) return false;
     if (((uintptr_t)g.samples) % 16 != 0 && !g.half_in) return false;
     return g.dbg == nullptr;
 }
@@ -545,8 +567,8 @@ static int launch_scatter_t(const GridLaunch &g, cudaStream_t s)
     }
     const unsigned samp = CH * (HALF ? 4u : 8u);
     /* longest run a spoke can have inside a tile's box: its diagonal (+ margins) */
-    const float bw = (float)(SC_T - 1) + 2.f * g.kb.W + 0.2f;
-    const unsigned longest = ((unsigned)(bw * 1.41421356f + 3.f) * samp + 31u) & ~15u;
+    const float bw = (float)(SC_T - 1) + 2.f * g.kb.W + 0.2f, bh = (float)(P::TH - 1) + 2.f * g.kb.W + 0.2f;
+    const unsigned longest = ((unsigned)(sqrtf(bw * bw + bh * bh) + 3.f) * samp + 31u) & ~15u;
     unsigned cap = getenv("TRON_SCATTER_CAP") ? (unsigned)atoi(getenv("TRON_SCATTER_CAP")) : 1536u;     /* 3 blocks per SM */
     if (cap < longest) cap = longest;
     cap = (cap + 127u) & ~127u;
@@ -576,6 +598,7 @@ int launch_grid_scatter(const GridLaunch &g, cudaStream_t s)
     case 2: return g.half_in ? launch_scatter_t<2, true>(g, s) : launch_scatter_t<2, false>(g, s);
     case 4: return g.half_in ? launch_scatter_t<4, true>(g, s) : launch_scatter_t<4, false>(g, s);
     case 6: return g.half_in ? launch_scatter_t<6, true>(g, s) : launch_scatter_t<6, false>(g, s);
+    case 16: return g.half_in ? launch_scatter_t<16, true>(g, s) : launch_scatter_t<16, false>(g, s);
     }
     return -1;
 }

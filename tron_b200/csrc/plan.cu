@@ -327,11 +327,11 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         /* tiles accumulated in shared memory, sample driven (grid_scatter.cu): the default where it applies */
         {
             const bool fits = p->kb.fast && cfg->kernwidth == 2.0f && g.nro == g.nxos && p->nch == g.nc
-                              && (g.nc == 2 || g.nc == 4 || g.nc == 6) && n % 16 == 0 && n <= 4096 && g.npe1work <= 4096;
+                              && (g.nc == 2 || g.nc == 4 || g.nc == 6 || g.nc == 16) && n % 16 == 0 && n <= 4096 && g.npe1work <= 4096;
             if (fits && !getenv("TRON_NO_SCATTER")) {
                 const int skip = cfg->skip_angles + (cfg->golden_angle ? g.slice_begin * g.prof_slide : 0);
                 PLAN_TRY(scatter_plan_build(p->scat, p->tabs.cells, p->tabs.nbins, n, p->nslices, g.npe1work, g.prof_slide,
-                                            skip, cfg->golden_angle, cfg->kernwidth, p->stream));
+                                            skip, cfg->golden_angle, cfg->kernwidth, g.nc, p->stream));
             }
         }
         PLAN_TRY(build_tile_schedule(&p->tile_sched8, &p->n_near8, n, 8,

@@ -48,6 +48,7 @@ struct ScatterPlan {
     int2 *tile_win = nullptr;                                /* packed angular-bin window per tile */
     int *sched = nullptr;                                    /* tiles (ty << 16 | tx): n_near, then n_far, then ntiles_empty */
     int win = 0, ne_delta = 0, per_slice = 0;
+    int th = 16;                                             /* tile height the windows and schedules were built for */
     int chain = 1, chain_near = 1;                           /* slices per chain for far / near tiles */
     int n_near = 0, n_far = 0, ntiles_empty = 0;
     int ready = 0;
@@ -109,7 +110,7 @@ int build_delta_tables(SpokeTables &d, const SpokeTables &full, int ntab, int ta
 bool grid_scatter_applicable(const GridLaunch &g);
 int launch_grid_scatter(const GridLaunch &g, cudaStream_t s);
 int scatter_plan_build(ScatterPlan &sp, const int2 *cells, int nbins, int n, int nslices, int win, int slide, int skip,
-                       int golden, float W, cudaStream_t s);
+                       int golden, float W, int nc, cudaStream_t s);
 void scatter_plan_free(ScatterPlan &sp);
 bool grid_wide_applicable(const GridLaunch &g);
 int launch_grid_wide(const GridLaunch &g, cudaStream_t s);
