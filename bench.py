@@ -388,7 +388,7 @@ def measure_adjoint_config(torch, t, name, local, steps=3, warmup=2, with_refere
     launches = plan.last_launches()
     e2e_ms = time_wall(torch, lambda: plan.recon_host_ptr(h_out.data_ptr(), h_in.data_ptr()), steps, 1)
     B = min(256, g["nz"])
-    kern = "grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel"
+    kern = "grid_scatter_kernel" if g["nc"] in (2, 4, 6, 16) else ("grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel")
     roof, grid_ms = grid_roofline(torch, plan, g, d_in, False, B, kern, name)
     roof["share_of_step"] = grid_ms * (g["nz"] / B) / ms
     out = {"workload": desc, "value": nsamp / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
@@ -646,16 +646,16 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (gridding), timed alone on this stream
     B = min(256, g["nz"])                                          # the launch length the device pipeline uses
-    kern = "grid_tile_kernel" if g["nc"] <= 8 else ("grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel")
+    kern = "grid_scatter_kernel" if g["nc"] in (2, 4, 6, 16) else ("grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel")
     roofline, grid_ms = grid_roofline(torch, plan, g, d_in, False, B, kern, args.workload)
     roofline["share_of_step"] = grid_ms * (g["nz"] / B) / ms_per_step
 
     extras = {}
     if not args.lean and args.workload == "cfg2":
         if world == 1:
-            # parity of THIS run's output against the unmodified reference (checker, untimed)
-            extras["parity"] = parity_vs_reference(torch, d_out, d_in, dims, flags, g, [0, 1, 31, 32, 477, 954, 955])
-            # cold span: what the reference's recon_radial2d brackets (tron.cu:726-786: init, buffers, recon,
+            # cold span FIRST (before the checker below maps the reference's library -- its own CUDA runtime, cuFFT,
+            # cuBLAS -- into this process: with it loaded every cudaMalloc/cudaFree here is ~5x slower,
+            # profiles/r02_cold_span.txt): what the reference's recon_radial2d brackets (tron.cu:726-786: init, buffers, recon,
             # shutdown) through the same-named legacy symbol = plan create + recon + destroy per call
             L = t.load_library()
             assert L.tron_set_config(C.byref(cfg)) == 0
@@ -669,6 +669,8 @@ def run_ours(args):
                                   "unit": "samples/s", "runs_ms": cold, "plan_create_ms_first": plan_create_ms,
                                   "how": "legacy recon_radial2d(h_out, h_in): tron_plan_create + tron_recon_host + "
                                          "tron_plan_destroy per call, CUDA context already up (as in the reference arm)"}
+            # parity of THIS run's output against the unmodified reference (checker, untimed)
+            extras["parity"] = parity_vs_reference(torch, d_out, d_in, dims, flags, g, [0, 1, 31, 32, 477, 954, 955])
         if world == 1:
             # the same job with fp16 storage at the boundary (north-star item 4): complex-half samples in,
             # complex-half images out, f32 arithmetic -- half the PCIe bytes in both directions

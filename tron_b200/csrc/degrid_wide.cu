@@ -69,9 +69,18 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
     const float inv_nro = rcp_approx((float)d.nro);
     const int chan0 = blockIdx.y * 32 * NCHUNK;
 
-    for (long long grp = (long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (long long)gridDim.x * 8) {
-        const int pe = (int)(grp / groups_per_spoke);
-        const int ro0 = (int)(grp - (long long)pe * groups_per_spoke) * DW_S;
+    /* Work order.  The 8 warps of a block take 8 ADJACENT SPOKES at the same radial position, and consecutive
+     * blocks walk outwards along that bundle: the few hundred blocks in flight then cover one thin bundle of
+     * spokes whose tap windows overlap (13 cells wide at -k 6, neighbouring spokes <= 1.6 cells apart), i.e. a
+     * footprint of ~20 MB that stays in the 126 MB L2, and the next bundle re-uses its inner part.  Walking
+     * along one spoke per warp instead (round 1) put ~560 MB of windows in flight at once: ncu measured 31.9 GB
+     * of DRAM reads for a 2.1 GB grid (profiles/r02_ncu_cfg5_wide.txt). */
+    const long long nwork = (long long)((d.npe + 7) / 8) * groups_per_spoke;
+    (void)ngroups;
+    for (long long wb = blockIdx.x; wb < nwork; wb += gridDim.x) {
+        const int pe = (int)(wb / groups_per_spoke) * 8 + warp;
+        const int ro0 = (int)(wb % groups_per_spoke) * DW_S;
+        if (pe >= d.npe) continue;
         const float2 cs = __ldg(d.cs + pe);
         /* coordinates of the four samples, exactly as tron.cu:554-561 compiles */
         float X[DW_S], Y[DW_S];
@@ -198,9 +207,8 @@ int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
     dim3 tg((unsigned)((ncell + 31) / 32), (unsigned)((d.nch + 31) / 32));
     planar_to_interleaved_kernel<<<tg, 256, 0, s>>>(scratch, d.grid, d.nch, ncell);
     TRON_CUDA(cudaGetLastError());
-    const long long ngroups = (long long)((d.nro + DW_S - 1) / DW_S) * d.npe;
-    int bx = (int)((ngroups + 7) / 8);
-    if (bx > 148 * 32) bx = 148 * 32;
+    const long long nwork = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 7) / 8);
+    int bx = (int)(nwork < 148 * 32 ? nwork : 148 * 32);
     if (d.nch % 64 == 0) {
         dim3 grid(bx, d.nch / 64);
         if (d.half_out) degrid_wide_kernel<2, true><<<grid, 256, 0, s>>>(d, scratch);

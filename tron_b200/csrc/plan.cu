@@ -197,6 +197,19 @@ static int clamp_batch_to_launch_limits(const tron_plan *p, int batch)
     return batch < 1 ? 1 : batch;
 }
 
+/* oversampled grid + pass-A output for `slices` slices per launch (never shrinks) */
+static int ensure_work_buffers(tron_plan *p, int slices)
+{
+    if (slices <= p->work_slices) return TRON_OK;
+    const int n = p->g.nxos;
+    cudaFree(p->d_grid); cudaFree(p->d_tmp);
+    p->d_grid = nullptr; p->d_tmp = nullptr; p->work_slices = 0;
+    TRON_CUDA(cudaMalloc(&p->d_grid, (size_t)(p->overlap ? 2 : 1) * slices * p->nch * n * n * sizeof(float2)));
+    TRON_CUDA(cudaMalloc(&p->d_tmp, (size_t)slices * p->nch * n * p->g.nx * sizeof(float2)));
+    p->work_slices = slices;
+    return TRON_OK;
+}
+
 extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
 {
     *out = nullptr;
@@ -359,8 +372,21 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         PLAN_CUDA(cudaMemset(p->grid_dbg, 0, (size_t)8 * 65536 * 8 * sizeof(long long)));
     }
     p->overlap = cfg->adjoint && !p->percoil && p->nslices > p->batch && getenv("TRON_OVERLAP") != nullptr;   /* measured slower on B200: off */
-    PLAN_CUDA(cudaMalloc(&p->d_grid, (size_t)(p->overlap ? 2 : 1) * p->batch * p->nch * n * n * sizeof(float2)));
-    PLAN_CUDA(cudaMalloc(&p->d_tmp, (size_t)p->batch * p->nch * n * g.nx * sizeof(float2)));
+    /* batch work buffers: sized for the host pipeline's launches now (<= HOST_BATCH_MAX slices: the cold span
+     * plan + recon + destroy then allocates and frees ~1.2 GB instead of ~4.8 GB), grown to the device path's
+     * launch length (p->batch) on its first use (ensure_work_buffers) */
+    {
+        int first = p->batch;
+        if (cfg->adjoint && !p->percoil && first > HOST_BATCH_MAX) {
+            int q = 1;
+            if (p->tabs.gs > 1) { q = p->tabs.gs * (p->chain > 0 ? p->chain : 1); if (p->scat.ready && p->scat.chain > q) q = p->scat.chain; }
+            first = (HOST_BATCH_MAX / q) * q;
+            if (first < q) first = q;
+            if (first > p->batch) first = p->batch;
+        }
+        int rc_w = ensure_work_buffers(p, first);
+        if (rc_w) { plan_release(p); return rc_w; }
+    }
     if (cfg->adjoint && !p->percoil && !p->overlap && getenv("TRON_FFT_FUSED")) {
         /* single-launch FFT stage (fft.cu: p2w_adj_fused): the intermediate lives in a ring of slices small
          * enough for the L2.  Measured on cfg2: HBM traffic of the stage 1605 -> 715 MB per 64 slices, but
@@ -510,11 +536,19 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     }
     const size_t spoke_bytes = (size_t)g.nc * g.nt * g.nro * p->in_elem_bytes;
     const size_t slice_out_bytes = (size_t)g.nx * g.ny * (p->cfg.per_coil_out ? (size_t)g.nc : 1) * p->out_elem_bytes;
-    const size_t grid_elems = (size_t)p->batch * p->nch * g.nxos * g.nxos;
     size_t spokes_up = 0;
     int i = 0;
     int gs = (p->tabs.gs > 0 ? p->tabs.gs : 1) * (p->chain > 0 ? p->chain : 1);   /* launch granularity */
     if (p->scat.ready && p->scat.chain > gs) gs = p->scat.chain;
+    /* slices per launch: the plan's batch on resident data, at most HOST_BATCH_MAX (TRON_HOST_BATCH) in host mode */
+    static const int hbm_env = getenv("TRON_HOST_BATCH") ? atoi(getenv("TRON_HOST_BATCH")) : 0;
+    const int hbm = hbm_env >= gs ? hbm_env : HOST_BATCH_MAX;
+    const int hb = host ? (p->batch < hbm ? p->batch : ((hbm / gs) * gs > 0 ? (hbm / gs) * gs : gs)) : p->batch;
+    {
+        const int rc_w = ensure_work_buffers(p, hb < p->batch ? hb : p->batch);
+        if (rc_w) return rc_w;
+    }
+    const size_t grid_elems = (size_t)p->work_slices * p->nch * g.nxos * g.nxos;
     /* TRON_HOST_TRACE: when did the last upload, the last kernel and the last download finish? */
     static const bool trace = getenv("TRON_HOST_TRACE") != nullptr;
     cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -525,9 +559,6 @@ static int run_adjoint_all(tron_plan *p, void *d_out, const void *d_in, cudaStre
     }
     for (int z0 = 0, nb = 0; z0 < p->nslices; z0 += nb, i ^= 1) {
         nb = p->nslices - z0 < p->batch ? p->nslices - z0 : p->batch;
-        static const int hbm_env = getenv("TRON_HOST_BATCH") ? atoi(getenv("TRON_HOST_BATCH")) : 0;
-        const int hbm = hbm_env >= gs ? hbm_env : HOST_BATCH_MAX;
-        const int hb = host ? (p->batch < hbm ? p->batch : (hbm / gs) * gs) : p->batch;
         if (host && nb > hb) nb = hb;
         if (host && hb >= 2 * gs) {
             /* host mode ramps the batch size up at the start and down at the end, so that the first

@@ -210,6 +210,7 @@ struct tron_plan {
     int chain = 0;                       /* slice groups per chain: the first is gridded in full, the others from differences */
     int zero_r2 = 0x7fffffff;            /* adjoint: cells beyond this squared radius never receive a sample */
     float2 *d_grid = nullptr, *d_tmp = nullptr;     /* batch work buffers */
+    int work_slices = 0;                            /* slices per launch they hold (grown on demand, plan.cu) */
     int *fft_sync = nullptr; int fft_ring = 0;      /* single-launch FFT stage: counters, slices of d_tmp used as a ring */
     float2 *d_gridi = nullptr;                      /* forward, nc >= 32: channel-interleaved copy of the grid */
     float2 *d_coil = nullptr;                       /* per-coil images of a batch (Walsh combine, CGNR iterate x) */
