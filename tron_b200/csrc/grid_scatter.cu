@@ -449,8 +449,11 @@ __device__ __forceinline__ void scatter_task(const GridLaunch &g, const ScatterP
                         ffma2(q0, w, v[2 * c]); ffma2(q1, w, v[2 * c + 1]);
                         sts_f4_if(ca, make_float4(q0.x, q0.y, q1.x, q1.y), ok);
                     }
-                    /* (no barrier between steps: the warp is converged here, its shared-memory instructions are
-                     * volatile and execute in program order, so the next step's loads see this step's stores) */
+#ifdef SC_STEP_SYNC
+                    __syncwarp();                           /* the next step's samples may tap the same cells */
+#endif
+                    /* (no barrier between steps by default: the warp is converged here, its shared-memory instructions
+                     * are volatile and execute in program order, so the next step's loads see this step's stores) */
                 }
             }
             __syncwarp();
