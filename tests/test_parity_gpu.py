@@ -592,6 +592,8 @@ def test_full_size_linearity_and_shard_consistency(lib):
     (64, dict(adjoint=True, golden=True, kernwidth=3.0)),                        # two channels per lane
     (48, dict(adjoint=True, golden=True, gridos=1.5)),                           # ragged last channel chunk
     (32, dict(adjoint=True, golden=True, undersamp=0.25, prof_slide=3, skip_angles=9)),
+    (16, dict(adjoint=True, golden=True, kernwidth=6.0)),                        # cfg5 shard on 4 GPUs: wide kernel for 16 coils
+    (16, dict(adjoint=True, kernwidth=3.5, undersamp=0.5, prof_slide=20)),
 ])
 def test_wide_channel_gridding_vs_reference(lib, reflib_wide, nc, flags):
     import tron_b200 as t
@@ -645,6 +647,9 @@ def test_wide_channel_fp16_storage(lib):
     (32, dict(adjoint=False, undersamp=0.5, skip_angles=3)),                     # linear angles
     (64, dict(adjoint=False, golden=True, kernwidth=6.0)),                       # cfg5 kernel width, 2 channels per lane
     (32, dict(adjoint=False, golden=True, kernwidth=2.5, undersamp=0.3)),
+    (16, dict(adjoint=False, golden=True, kernwidth=6.0)),                       # cfg5 shard on 4 GPUs: two rows per warp step
+    (8, dict(adjoint=False, kernwidth=6.0, undersamp=0.7)),                      # cfg5 shard on 8 GPUs: four rows per warp step
+    (16, dict(adjoint=False, golden=True, kernwidth=3.0, skip_angles=2)),
 ])
 def test_wide_channel_degridding_vs_reference(lib, reflib, nc, flags):
     """Forward path with nc >= 32 (lanes = channels kernel) against the reference and the thread-per-sample kernel."""

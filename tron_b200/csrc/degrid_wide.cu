@@ -30,8 +30,8 @@ namespace tronb {
 struct __align__(16) DwWeights {
     float4 wx[DW_MAXU];   /* row factor of samples 0..3 */
     float4 wy[DW_MAXU];   /* column factor */
-    float4 wp[DW_MAXU];   /* wx[i] * wy[j] of the current row: formed once per row by lanes j < nuy, so the
-                             channel loop reads the finished tap weight instead of multiplying per cell */
+    float4 wp[4][DW_MAXU];/* wx[i] * wy[j] of the rows in flight (one per sub-warp, see LPC): formed once per row by lanes
+                             j < nuy, so the channel loop reads the finished tap weight instead of multiplying per cell */
     int coff[DW_MAXU + 4];/* element offset of every column of the union window: the periodic wrap is applied once
                              per column here instead of an integer modulo per cell (ncu: 45 -> 25 instructions per
                              cell, cfg5 forward 18.4 -> 13.6 ms); padded by repeating the last column */
@@ -54,10 +54,15 @@ __device__ __forceinline__ float2 ldg2v(const float2 *p)
     return v;
 }
 
-template <int NCHUNK, bool HALF>
+/* LPC = lanes per cell = channels fetched by one request.  32 (or 64 channels with NCHUNK = 2): the warp walks the
+ * rows of the union window one by one.  16 / 8 (coil shards of a many-coil job, cfg5 on 4 / 8 GPUs): the warp's
+ * 2 / 4 sub-warps take 2 / 4 rows at a time -- every lane still owns a channel, every request is still a whole
+ * 128- / 64-byte piece -- and their partial sums are added by shuffles at the end. */
+template <int NCHUNK, bool HALF, int LPC>
 __global__ void __launch_bounds__(256)
 degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interleaved grid */)
 {
+    constexpr int RPI = 32 / LPC;                    /* rows in flight per warp */
     __shared__ DwWeights sw[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     DwWeights &S = sw[warp];
@@ -68,6 +73,7 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
     const float c0 = (float)((n + 1) / 2);
     const float inv_nro = rcp_approx((float)d.nro);
     const int chan0 = blockIdx.y * 32 * NCHUNK;
+    const int clane = lane % LPC, rsub = lane / LPC; /* channel lane, sub-warp (row) */
 
     /* Work order.  The 8 warps of a block take 8 ADJACENT SPOKES at the same radial position, and consecutive
      * blocks walk outwards along that bundle: the few hundred blocks in flight then cover one thin bundle of
@@ -126,16 +132,20 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
         for (int c = 0; c < NCHUNK; ++c)
 #pragma unroll
             for (int s = 0; s < DW_S; ++s) acc[c][s] = make_float2(0.f, 0.f);
-        for (int i = 0; i < nux; ++i) {
-            const float4 a = S.wx[i];
+        for (int i0 = 0; i0 < nux; i0 += RPI) {
             __syncwarp();
-            if (lane < nuy) {
-                const float4 b = S.wy[lane];
-                S.wp[lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+#pragma unroll
+            for (int rr = 0; rr < RPI; ++rr) {
+                const float4 a = i0 + rr < nux ? S.wx[i0 + rr] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < nuy) {
+                    const float4 b = S.wy[lane];
+                    S.wp[rr][lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+                }
             }
             __syncwarp();
+            const int i = min(i0 + rsub, nux - 1);                          /* (rows past the window: zero weights) */
             const int row = (xlo + i + n) % n;                              /* periodic, tron.cu:569 */
-            const float2 *grow = gi + ((size_t)row * n) * nch + chan0 + lane;
+            const float2 *grow = gi + ((size_t)row * n) * nch + chan0 + clane;
             for (int j0 = 0; j0 < nuy; j0 += 4) {
                 float2 v[4][NCHUNK];
 #pragma unroll
@@ -147,7 +157,7 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     if (j0 + jj < nuy) {
-                        const float4 b = S.wp[j0 + jj];
+                        const float4 b = S.wp[rsub][j0 + jj];
                         const float w0 = b.x, w1 = b.y, w2 = b.z, w3 = b.w;
 #pragma unroll
                         for (int c = 0; c < NCHUNK; ++c) {
@@ -158,13 +168,24 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
                 }
             }
         }
+        if (RPI > 1) {                                                      /* add the sub-warps' partial sums */
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+                for (int s = 0; s < DW_S; ++s)
+#pragma unroll
+                    for (int o = LPC; o < 32; o <<= 1) {
+                        acc[c][s].x += __shfl_xor_sync(0xffffffffu, acc[c][s].x, o);
+                        acc[c][s].y += __shfl_xor_sync(0xffffffffu, acc[c][s].y, o);
+                    }
+        }
 #pragma unroll
         for (int s = 0; s < DW_S; ++s) {
             if (ro0 + s >= d.nro) continue;
-            const size_t base = ((size_t)pe * d.nro + ro0 + s) * d.nc_total + d.ch0 + chan0 + lane;
+            const size_t base = ((size_t)pe * d.nro + ro0 + s) * d.nc_total + d.ch0 + chan0 + clane;
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
-                if (chan0 + c * 32 + lane >= nch) continue;
+                if (rsub != 0 || chan0 + c * 32 + clane >= nch) continue;
                 if (HALF) ((__half2 *)d.samples)[base + c * 32] = __float22half2_rn(acc[c][s]);
                 else ((float2 *)d.samples)[base + c * 32] = acc[c][s];
             }
@@ -195,7 +216,10 @@ planar_to_interleaved_kernel(float2 *__restrict__ dst, const float2 *__restrict_
 
 bool degrid_wide_applicable(const DegridLaunch &d)
 {
-    if (d.nch < 32 || d.nch % 32 != 0) return false;
+    /* 8 or 16 channels: the thread-per-sample kernel wins for narrow kernels; from W = 3 on (cfg5's coil shards,
+     * -k 6: 18.0 ms for a 16-coil 2048^2 shard) the shared window does */
+    const bool few = (d.nch == 8 || d.nch == 16) && d.kb.W >= 3.f;
+    if (!few && (d.nch < 32 || d.nch % 32 != 0)) return false;
     if ((int)floorf(2.f * d.kb.W) + 1 + DW_S - 1 + 1 > DW_MAXU) return false;
     return true;
 }
@@ -209,14 +233,20 @@ int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
     TRON_CUDA(cudaGetLastError());
     const long long nwork = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 7) / 8);
     int bx = (int)(nwork < 148 * 32 ? nwork : 148 * 32);
-    if (d.nch % 64 == 0) {
+    if (d.nch == 8) {
+        if (d.half_out) degrid_wide_kernel<1, true, 8><<<bx, 256, 0, s>>>(d, scratch);
+        else            degrid_wide_kernel<1, false, 8><<<bx, 256, 0, s>>>(d, scratch);
+    } else if (d.nch == 16) {
+        if (d.half_out) degrid_wide_kernel<1, true, 16><<<bx, 256, 0, s>>>(d, scratch);
+        else            degrid_wide_kernel<1, false, 16><<<bx, 256, 0, s>>>(d, scratch);
+    } else if (d.nch % 64 == 0) {
         dim3 grid(bx, d.nch / 64);
-        if (d.half_out) degrid_wide_kernel<2, true><<<grid, 256, 0, s>>>(d, scratch);
-        else            degrid_wide_kernel<2, false><<<grid, 256, 0, s>>>(d, scratch);
+        if (d.half_out) degrid_wide_kernel<2, true, 32><<<grid, 256, 0, s>>>(d, scratch);
+        else            degrid_wide_kernel<2, false, 32><<<grid, 256, 0, s>>>(d, scratch);
     } else {
         dim3 grid(bx, d.nch / 32);
-        if (d.half_out) degrid_wide_kernel<1, true><<<grid, 256, 0, s>>>(d, scratch);
-        else            degrid_wide_kernel<1, false><<<grid, 256, 0, s>>>(d, scratch);
+        if (d.half_out) degrid_wide_kernel<1, true, 32><<<grid, 256, 0, s>>>(d, scratch);
+        else            degrid_wide_kernel<1, false, 32><<<grid, 256, 0, s>>>(d, scratch);
     }
     TRON_CUDA(cudaGetLastError());
     return 0;

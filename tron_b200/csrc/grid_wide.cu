@@ -330,7 +330,10 @@ static int launch_wide(GridLaunch g, cudaStream_t s)
 bool grid_wide_applicable(const GridLaunch &g)
 {
     /* nc = 16 is faster on the thread-per-cell kernel (measured: 9.3 vs 18.3 us/slice on cfg4) */
-    if (g.nch < 32 || g.nch % 16 != 0) return false;
+    /* ... for the default kernel width; with wide kernels (cfg5's 16-coil shards at -k 6) a sample serves dozens of
+     * blocks and fetching it once per block wins again */
+    const bool few = g.nch == 16 && g.kb.W >= 3.f;
+    if (!few && (g.nch < 32 || g.nch % 16 != 0)) return false;
     if (g.n % 4 != 0) return false;
     if (g.gs != 1 && g.gs != 4) return false;
     /* sample offsets inside a table's window are 32-bit element counts: (window spokes * nro) * nc must fit */

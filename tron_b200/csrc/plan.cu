@@ -398,7 +398,7 @@ extern "C" int tron_plan_create(tron_plan **out, const tron_config *cfg)
         p->fft_ring = ring;
         PLAN_CUDA(cudaMalloc(&p->fft_sync, 2 * (size_t)p->batch * sizeof(int)));
     }
-    if (!cfg->adjoint && p->nch >= 32 && p->nch % 32 == 0)
+    if (!cfg->adjoint && ((p->nch >= 32 && p->nch % 32 == 0) || ((p->nch == 8 || p->nch == 16) && cfg->kernwidth >= 3.f)))
         PLAN_CUDA(cudaMalloc(&p->d_gridi, (size_t)p->nch * n * n * sizeof(float2)));
     if (p->percoil) {
         const size_t N = (size_t)p->batch * g.nc * g.nx * g.nx, ns = (size_t)p->batch * g.nc * g.nro * g.npe1work;
