@@ -78,3 +78,54 @@ def test_coil_shard_bookkeeping(lib):
             seen += list(range(g.coil_begin, g.coil_end))
             assert g.nxos == 2048 and g.nx == 1024
         assert seen == list(range(64))
+
+
+def _coil_worker(rank, world, port, q):
+    """Coil-sharded root sum of squares, host protocol on CPU: every rank forms the partial sum of squares of ITS
+    coils (the CPU oracle's per-coil adjoint stands in for the GPU pipeline with sos_partial), one reduce(sum)
+    to rank 0 -- the collective tron_coil_reduce issues as ncclReduce -- and sqrt there equal the one-process
+    coilcombinesos image (tron.cu:255-268)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    import tron_b200 as t
+    from oracle.oracle import Oracle
+    from util import synth_complex
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nc, nro, npe = 4, 32, 24
+        dims = [nc, 1, nro, npe, 1]
+        per = nc // world
+        g = t.geometry(t.make_config(dims, adjoint=True, golden=True, coils=(rank * per, (rank + 1) * per), sos_partial=True))
+        assert (g.coil_begin, g.coil_end) == (rank * per, (rank + 1) * per)
+        assert int(g.shard_out_elems) == g.nx * g.ny                       # one float per pixel and slice
+        o = Oracle()
+        x = synth_complex((npe, nro, nc), stream=91)
+        mine = np.ascontiguousarray(x[:, :, g.coil_begin:g.coil_end])
+        cfg = o.config([per, 1, nro, npe, 1], True, golden=True)
+        coil_imgs = o.adj_coils(cfg, mine)                                  # (nx, nx, per) per-coil images
+        sos = torch.from_numpy((np.abs(coil_imgs.astype(np.complex128)) ** 2).sum(axis=2).astype(np.float32).ravel())
+        dist.reduce(sos, dst=0, op=dist.ReduceOp.SUM)                       # the one collective of the path
+        if rank == 0:
+            got = np.sqrt(sos.numpy())
+            want = o.recon(o.config(dims, True, golden=True), x.ravel()).real
+            err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+            q.put(err)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_coil_sharded_sum_of_squares_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_coil_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert q.get(timeout=10) <= 1e-6
