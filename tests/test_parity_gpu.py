@@ -669,6 +669,17 @@ def test_wide_channel_degridding_vs_reference(lib, reflib, nc, flags):
     finally:
         del os.environ["TRON_NO_WIDE"]
     assert rel_l2(got, other) <= 2e-6
+    # one and two spokes per warp (the default pairs spokes only for linear angle order; forced on a golden-angle
+    # order the pairs are not neighbours and the kernel must walk them spoke by spoke)
+    for pair in ("0", "1"):
+        os.environ["TRON_DEGRID_PAIR"] = pair
+        try:
+            with t.Plan(flags_to_cfg(dims, flags)) as p:
+                other = p.recon_host(h_in)
+        finally:
+            del os.environ["TRON_DEGRID_PAIR"]
+        assert rel_l2(other, want) <= TOL_F32, (pair, rel_l2(other, want))
+        assert np.array_equal(other != 0, want != 0)
 
 
 def test_shepp_logan_round_trip(lib, reflib):

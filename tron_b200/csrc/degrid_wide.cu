@@ -21,20 +21,22 @@
  * planar_to_interleaved_kernel); output: samples[(pe*nro + ro)*nc_total + ch0 + ch].
  */
 #include "tron_internal.h"
+#include <stdlib.h>
 
 namespace tronb {
 
 #define DW_S 4            /* samples per warp */
 #define DW_MAXU 20        /* union window side: floor(2W)+1 + DW_S-1 + slack <= 20  (W <= 7.5) */
 
-struct __align__(16) DwWeights {
-    float4 wx[DW_MAXU];   /* row factor of samples 0..3 */
-    float4 wy[DW_MAXU];   /* column factor */
-    float4 wp[4][DW_MAXU];/* wx[i] * wy[j] of the rows in flight (one per sub-warp, see LPC): formed once per row by lanes
-                             j < nuy, so the channel loop reads the finished tap weight instead of multiplying per cell */
-    int coff[DW_MAXU + 4];/* element offset of every column of the union window: the periodic wrap is applied once
-                             per column here instead of an integer modulo per cell (ncu: 45 -> 25 instructions per
-                             cell, cfg5 forward 18.4 -> 13.6 ms); padded by repeating the last column */
+/* P = spokes per warp (DW_S samples each) */
+template <int P> struct __align__(16) DwWeights {
+    float4 wx[P][DW_MAXU];   /* row factor of samples 0..3 of spoke p */
+    float4 wy[P][DW_MAXU];   /* column factor */
+    float4 wp[4][P][DW_MAXU];/* wx[i] * wy[j] of the rows in flight (one per sub-warp, see LPC): formed once per row by lanes
+                                j < nuy, so the channel loop reads the finished tap weight instead of multiplying per cell */
+    int coff[DW_MAXU + 8];   /* wrapped index of every column of the union window: the periodic wrap is applied once
+                                per column here instead of an integer modulo per cell (ncu: 45 -> 25 instructions per
+                                cell, cfg5 forward 18.4 -> 13.6 ms); padded by repeating the last column */
 };
 
 __device__ __forceinline__ void ffma2d(float2 &acc, float w, float2 v)
@@ -54,117 +56,208 @@ __device__ __forceinline__ float2 ldg2v(const float2 *p)
     return v;
 }
 
+/* the NCHUNK adjacent channels a lane holds of one grid cell: one 8- or 16-byte request */
+template <int NCHUNK>
+__device__ __forceinline__ void ldg_cell(float2 (&v)[NCHUNK], const char *p)
+{
+    if (NCHUNK == 2) {
+        asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[NCHUNK - 1].x), "=f"(v[NCHUNK - 1].y) : "l"(p));
+    } else {
+        v[0] = ldg2v((const float2 *)p);
+    }
+}
+
+template <int NCHUNK, bool HALF, int NS>
+__device__ __forceinline__ void store_chan(void *samples, size_t base, const float2 (&acc)[NCHUNK][NS], int s)
+{
+    if (HALF) {
+        if (NCHUNK == 2) {
+            const __half2 a = __float22half2_rn(acc[0][s]), b = __float22half2_rn(acc[NCHUNK - 1][s]);
+            uint2 u = make_uint2(*reinterpret_cast<const unsigned *>(&a), *reinterpret_cast<const unsigned *>(&b));
+            *reinterpret_cast<uint2 *>((__half2 *)samples + base) = u;
+        } else ((__half2 *)samples)[base] = __float22half2_rn(acc[0][s]);
+    } else {
+        if (NCHUNK == 2)
+            *reinterpret_cast<float4 *>((float2 *)samples + base) =
+                make_float4(acc[0][s].x, acc[0][s].y, acc[NCHUNK - 1][s].x, acc[NCHUNK - 1][s].y);
+        else ((float2 *)samples)[base] = acc[0][s];
+    }
+}
+
+/* (u + n) % n of tron.cu:569-570 for -n <= u < 2n (taps reach at most W < n cells past the grid) */
+__device__ __forceinline__ int wrap_cell_w(int u, int n)
+{
+    u += u < 0 ? n : 0;
+    return u - (u >= n ? n : 0);
+}
+
+/* four neighbouring columns of one grid row */
+template <int NCHUNK>
+__device__ __forceinline__ void load_quad(float2 (&v)[4][NCHUNK], const char *grow, const int *coff, unsigned cstride)
+{
+    const int4 co = *reinterpret_cast<const int4 *>(coff);
+    ldg_cell<NCHUNK>(v[0], grow + (unsigned long long)(unsigned)co.x * cstride);
+    ldg_cell<NCHUNK>(v[1], grow + (unsigned long long)(unsigned)co.y * cstride);
+    ldg_cell<NCHUNK>(v[2], grow + (unsigned long long)(unsigned)co.z * cstride);
+    ldg_cell<NCHUNK>(v[3], grow + (unsigned long long)(unsigned)co.w * cstride);
+}
+
+template <int NCHUNK, int P>
+__device__ __forceinline__ void fma_quad(float2 (&acc)[NCHUNK][P * 4], const float2 (&v)[4][NCHUNK], const float4 *w /* [P][DW_MAXU] */)
+{
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float4 b = w[p * DW_MAXU + jj];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                ffma2d(acc[c][4 * p + 0], b.x, v[jj][c]); ffma2d(acc[c][4 * p + 1], b.y, v[jj][c]);
+                ffma2d(acc[c][4 * p + 2], b.z, v[jj][c]); ffma2d(acc[c][4 * p + 3], b.w, v[jj][c]);
+            }
+        }
+    }
+}
+
 /* LPC = lanes per cell = channels fetched by one request.  32 (or 64 channels with NCHUNK = 2): the warp walks the
  * rows of the union window one by one.  16 / 8 (coil shards of a many-coil job, cfg5 on 4 / 8 GPUs): the warp's
  * 2 / 4 sub-warps take 2 / 4 rows at a time -- every lane still owns a channel, every request is still a whole
  * 128- / 64-byte piece -- and their partial sums are added by shuffles at the end. */
-template <int NCHUNK, bool HALF, int LPC>
+template <int NCHUNK, bool HALF, int LPC, int P>
 __global__ void __launch_bounds__(256)
 degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interleaved grid */)
 {
     constexpr int RPI = 32 / LPC;                    /* rows in flight per warp */
-    __shared__ DwWeights sw[8];
+    constexpr int NS = P * DW_S;                     /* samples per warp: s = DW_S * spoke + position */
+    __shared__ DwWeights<P> sw[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    DwWeights &S = sw[warp];
+    DwWeights<P> &S = sw[warp];
     const int n = d.n, nch = d.nch;
     const int groups_per_spoke = (d.nro + DW_S - 1) / DW_S;
-    const long long ngroups = (long long)groups_per_spoke * d.npe;
     const float W = d.kb.W;
     const float c0 = (float)((n + 1) / 2);
     const float inv_nro = rcp_approx((float)d.nro);
     const int chan0 = blockIdx.y * 32 * NCHUNK;
     const int clane = lane % LPC, rsub = lane / LPC; /* channel lane, sub-warp (row) */
+    const unsigned cstride = (unsigned)nch * (unsigned)sizeof(float2);   /* bytes between neighbouring columns */
 
-    /* Work order.  The 8 warps of a block take 8 ADJACENT SPOKES at the same radial position, and consecutive
+    /* Work order.  The 8 warps of a block take 8 P ADJACENT SPOKES at the same radial position, and consecutive
      * blocks walk outwards along that bundle: the few hundred blocks in flight then cover one thin bundle of
      * spokes whose tap windows overlap (13 cells wide at -k 6, neighbouring spokes <= 1.6 cells apart), i.e. a
      * footprint of ~20 MB that stays in the 126 MB L2, and the next bundle re-uses its inner part.  Walking
      * along one spoke per warp instead (round 1) put ~560 MB of windows in flight at once: ncu measured 31.9 GB
-     * of DRAM reads for a 2.1 GB grid (profiles/r02_ncu_cfg5_wide.txt). */
-    const long long nwork = (long long)((d.npe + 7) / 8) * groups_per_spoke;
-    (void)ngroups;
+     * of DRAM reads for a 2.1 GB grid (profiles/r02_ncu_cfg5_wide.txt).
+     * P = 2 (linear angle order: spokes pe, pe + 1 are neighbours): the warp's union window barely grows, a loaded
+     * cell feeds 8 samples instead of 4 -- the kernel is bound by L1 wavefronts (ncu: l1tex 79 %, a 64-channel cell
+     * is 4 wavefronts + 1 for its weights per 8 FFMA2), so cells per sample is what counts.  A pair whose union
+     * window would not fit (spokes that are NOT neighbours) is walked spoke by spoke. */
+    const long long nwork = (long long)((d.npe + 8 * P - 1) / (8 * P)) * groups_per_spoke;
     for (long long wb = blockIdx.x; wb < nwork; wb += gridDim.x) {
-        const int pe = (int)(wb / groups_per_spoke) * 8 + warp;
+        const int pe0 = ((int)(wb / groups_per_spoke) * 8 + warp) * P;
         const int ro0 = (int)(wb % groups_per_spoke) * DW_S;
-        if (pe >= d.npe) continue;
-        const float2 cs = __ldg(d.cs + pe);
-        /* coordinates of the four samples, exactly as tron.cu:554-561 compiles */
-        float X[DW_S], Y[DW_S];
-        int xlo = 1 << 30, xhi = -(1 << 30), ylo = 1 << 30, yhi = -(1 << 30);
+        if (pe0 >= d.npe) continue;
+        /* coordinates of the samples, exactly as tron.cu:554-561 compiles */
+        float X[NS], Y[NS];
+        int bx0[P], bx1[P], by0[P], by1[P];
 #pragma unroll
-        for (int s = 0; s < DW_S; ++s) {
-            const float R = fma_ftz((float)(ro0 + s), inv_nro, -0.5f);
-            const float nR = mul_ftz(R, (float)n);
-            X[s] = fma_ftz(cs.y, nR, c0);            /* rows:    sin */
-            Y[s] = fma_ftz(cs.x, nR, c0);            /* columns: cos */
-            if (ro0 + s < d.nro) {
-                xlo = min(xlo, (int)ceilf(X[s] - W)); xhi = max(xhi, (int)floorf(X[s] + W));
-                ylo = min(ylo, (int)ceilf(Y[s] - W)); yhi = max(yhi, (int)floorf(Y[s] + W));
+        for (int p = 0; p < P; ++p) {
+            const float2 cs = __ldg(d.cs + min(pe0 + p, d.npe - 1));
+            bx0[p] = by0[p] = 1 << 30; bx1[p] = by1[p] = -(1 << 30);
+#pragma unroll
+            for (int k = 0; k < DW_S; ++k) {
+                const int s = p * DW_S + k;
+                const float R = fma_ftz((float)(ro0 + k), inv_nro, -0.5f);
+                const float nR = mul_ftz(R, (float)n);
+                X[s] = fma_ftz(cs.y, nR, c0);            /* rows:    sin */
+                Y[s] = fma_ftz(cs.x, nR, c0);            /* columns: cos */
+                if (ro0 + k < d.nro && pe0 + p < d.npe) {
+                    bx0[p] = min(bx0[p], (int)ceilf(X[s] - W)); bx1[p] = max(bx1[p], (int)floorf(X[s] + W));
+                    by0[p] = min(by0[p], (int)ceilf(Y[s] - W)); by1[p] = max(by1[p], (int)floorf(Y[s] + W));
+                }
             }
         }
-        const int nux = min(xhi - xlo + 1, DW_MAXU), nuy = min(yhi - ylo + 1, DW_MAXU);
-
-        /* phase A: lanes 0..nux-1 rows, the others (offset 16 would not cover 20) -> two passes */
-        __syncwarp();
-        for (int i = lane; i < nux + nuy; i += 32) {
-            const bool isrow = i < nux;
-            const int u = isrow ? xlo + i : ylo + (i - nux);
-            float w4[DW_S];
+        /* one pass over the union window of all spokes if it fits, else one pass per spoke */
+        int npass = 1;
+        if (P > 1) {
+            int x0 = bx0[0], x1 = bx1[0], y0 = by0[0], y1 = by1[0];
 #pragma unroll
-            for (int s = 0; s < DW_S; ++s) {
-                const float dd = (float)u - (isrow ? X[s] : Y[s]);
-                const bool live = (ro0 + s < d.nro) && fabsf(dd) < W;     /* tron.cu:343 via gridkernel */
-                w4[s] = live ? kb_weight(dd, d.kb) : 0.f;
-            }
-            if (isrow) S.wx[i] = make_float4(w4[0], w4[1], w4[2], w4[3]);
-            else {
-                S.wy[i - nux] = make_float4(w4[0], w4[1], w4[2], w4[3]);
-                const int off = ((u + n) % n) * nch;                           /* periodic, tron.cu:570 */
-                S.coff[i - nux] = off;
-                if (i - nux == nuy - 1) { S.coff[nuy] = off; S.coff[nuy + 1] = off; S.coff[nuy + 2] = off; }
-            }
+            for (int p = 1; p < P; ++p) { x0 = min(x0, bx0[p]); x1 = max(x1, bx1[p]); y0 = min(y0, by0[p]); y1 = max(y1, by1[p]); }
+            if (x1 - x0 + 1 > DW_MAXU || y1 - y0 + 1 > DW_MAXU) npass = P;
         }
-        __syncwarp();
 
-        /* phase B: lanes = channels */
-        float2 acc[NCHUNK][DW_S];
+        float2 acc[NCHUNK][NS];
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c)
 #pragma unroll
-            for (int s = 0; s < DW_S; ++s) acc[c][s] = make_float2(0.f, 0.f);
-        for (int i0 = 0; i0 < nux; i0 += RPI) {
-            __syncwarp();
+            for (int s = 0; s < NS; ++s) acc[c][s] = make_float2(0.f, 0.f);
+
+        for (int pass = 0; pass < npass; ++pass) {
+            int xlo = 1 << 30, xhi = -(1 << 30), ylo = 1 << 30, yhi = -(1 << 30);
 #pragma unroll
-            for (int rr = 0; rr < RPI; ++rr) {
-                const float4 a = i0 + rr < nux ? S.wx[i0 + rr] : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < nuy) {
-                    const float4 b = S.wy[lane];
-                    S.wp[rr][lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+            for (int p = 0; p < P; ++p)
+                if (npass == 1 || p == pass) {
+                    xlo = min(xlo, bx0[p]); xhi = max(xhi, bx1[p]); ylo = min(ylo, by0[p]); yhi = max(yhi, by1[p]);
                 }
+            if (xhi < xlo) continue;                                            /* (a spoke past the last one) */
+            const int nux = min(xhi - xlo + 1, DW_MAXU), nuy = min(yhi - ylo + 1, DW_MAXU);
+
+            /* phase A: lanes 0..nux-1 rows, the others (offset 16 would not cover 20) -> two passes */
+            const int nuy4 = (nuy + 3) & ~3;                                    /* columns in whole quads: <= DW_MAXU */
+            __syncwarp();
+            for (int i = lane; i < nux + nuy4; i += 32) {
+                const bool isrow = i < nux;
+                const int u = isrow ? xlo + i : ylo + min(i - nux, nuy - 1);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    float w4[DW_S];
+#pragma unroll
+                    for (int k = 0; k < DW_S; ++k) {
+                        const int s = p * DW_S + k;
+                        const float dd = (float)u - (isrow ? X[s] : Y[s]);
+                        const bool live = (ro0 + k < d.nro) && (pe0 + p < d.npe) && (npass == 1 || p == pass)
+                            && fabsf(dd) < W && (isrow || i - nux < nuy);        /* tron.cu:343 via gridkernel */
+                        w4[k] = live ? kb_weight(dd, d.kb) : 0.f;
+                    }
+                    /* the pad columns of the last quad repeat the last column with zero weights (no new address) */
+                    if (isrow) S.wx[p][i] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+                    else S.wy[p][i - nux] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                if (!isrow) S.coff[i - nux] = wrap_cell_w(u, n);                 /* periodic, tron.cu:570 */
             }
+            if (lane < 8) S.coff[nuy4 + lane] = wrap_cell_w(ylo + nuy - 1, n);
             __syncwarp();
-            const int i = min(i0 + rsub, nux - 1);                          /* (rows past the window: zero weights) */
-            const int row = (xlo + i + n) % n;                              /* periodic, tron.cu:569 */
-            const float2 *grow = gi + ((size_t)row * n) * nch + chan0 + clane;
-            for (int j0 = 0; j0 < nuy; j0 += 4) {
-                float2 v[4][NCHUNK];
+
+            /* phase B: lanes = channels (NCHUNK = 2: lane l holds channels 2l, 2l + 1 of the CTA's 64 -- one 16-byte load) */
+            for (int i0 = 0; i0 < nux; i0 += RPI) {
+                __syncwarp();
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int co = S.coff[j0 + jj];
+                for (int rr = 0; rr < RPI; ++rr)
 #pragma unroll
-                    for (int c = 0; c < NCHUNK; ++c) v[jj][c] = ldg2v(grow + co + c * 32);
-                }
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    if (j0 + jj < nuy) {
-                        const float4 b = S.wp[rsub][j0 + jj];
-                        const float w0 = b.x, w1 = b.y, w2 = b.z, w3 = b.w;
-#pragma unroll
-                        for (int c = 0; c < NCHUNK; ++c) {
-                            ffma2d(acc[c][0], w0, v[jj][c]); ffma2d(acc[c][1], w1, v[jj][c]);
-                            ffma2d(acc[c][2], w2, v[jj][c]); ffma2d(acc[c][3], w3, v[jj][c]);
+                    for (int p = 0; p < P; ++p) {
+                        const float4 a = i0 + rr < nux ? S.wx[p][i0 + rr] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (lane < nuy4) {
+                            const float4 b = S.wy[p][lane];
+                            S.wp[rr][p][lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
                         }
                     }
+                __syncwarp();
+                const int i = min(i0 + rsub, nux - 1);                          /* (rows past the window: zero weights) */
+                const int row = wrap_cell_w(xlo + i, n);                        /* periodic, tron.cu:569 */
+                const char *grow = (const char *)(gi + ((size_t)row * n) * nch + chan0 + clane * NCHUNK);
+                const float4 *wrow = &S.wp[rsub][0][0];
+                asm volatile("mov.b64 %0, %0;" : "+l"(grow));      /* one register pair: no uniform part added per address */
+                /* the next quad of cells is in flight while this one is consumed (ptxas otherwise pairs every load with
+                 * its first use); a column's address is one IMAD.WIDE: wrapped column index x cell stride + row base.
+                 * (past the last quad: coff is padded with the last column, those loads are discarded) */
+                float2 va[4][NCHUNK], vb[4][NCHUNK];
+                load_quad<NCHUNK>(va, grow, &S.coff[0], cstride);
+                for (int j0 = 0; j0 < nuy4; j0 += 8) {
+                    load_quad<NCHUNK>(vb, grow, &S.coff[j0 + 4], cstride);
+                    fma_quad<NCHUNK, P>(acc, va, wrow + j0);
+                    if (j0 + 4 >= nuy4) break;
+                    load_quad<NCHUNK>(va, grow, &S.coff[j0 + 8], cstride);
+                    fma_quad<NCHUNK, P>(acc, vb, wrow + j0 + 4);
                 }
             }
         }
@@ -172,22 +265,20 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c)
 #pragma unroll
-                for (int s = 0; s < DW_S; ++s)
+                for (int s = 0; s < NS; ++s)
 #pragma unroll
                     for (int o = LPC; o < 32; o <<= 1) {
                         acc[c][s].x += __shfl_xor_sync(0xffffffffu, acc[c][s].x, o);
                         acc[c][s].y += __shfl_xor_sync(0xffffffffu, acc[c][s].y, o);
                     }
         }
+        if (rsub == 0 && chan0 + clane * NCHUNK < nch) {
 #pragma unroll
-        for (int s = 0; s < DW_S; ++s) {
-            if (ro0 + s >= d.nro) continue;
-            const size_t base = ((size_t)pe * d.nro + ro0 + s) * d.nc_total + d.ch0 + chan0 + clane;
-#pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                if (rsub != 0 || chan0 + c * 32 + clane >= nch) continue;
-                if (HALF) ((__half2 *)d.samples)[base + c * 32] = __float22half2_rn(acc[c][s]);
-                else ((float2 *)d.samples)[base + c * 32] = acc[c][s];
+            for (int s = 0; s < NS; ++s) {
+                const int pe = pe0 + s / DW_S, ro = ro0 + s % DW_S;
+                if (ro >= d.nro || pe >= d.npe) continue;
+                const size_t base = ((size_t)pe * d.nro + ro) * d.nc_total + d.ch0 + chan0 + clane * NCHUNK;
+                store_chan<NCHUNK, HALF, NS>(d.samples, base, acc, s);
             }
         }
     }
@@ -224,6 +315,13 @@ bool degrid_wide_applicable(const DegridLaunch &d)
     return true;
 }
 
+template <int NCHUNK, int LPC, int P>
+static void launch_dw(const DegridLaunch &d, const float2 *scratch, dim3 grid, cudaStream_t s)
+{
+    if (d.half_out) degrid_wide_kernel<NCHUNK, true, LPC, P><<<grid, 256, 0, s>>>(d, scratch);
+    else            degrid_wide_kernel<NCHUNK, false, LPC, P><<<grid, 256, 0, s>>>(d, scratch);
+}
+
 /* scratch: nch*n*n float2, receives the channel-interleaved copy of the planar grid */
 int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
 {
@@ -231,22 +329,23 @@ int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
     dim3 tg((unsigned)((ncell + 31) / 32), (unsigned)((d.nch + 31) / 32));
     planar_to_interleaved_kernel<<<tg, 256, 0, s>>>(scratch, d.grid, d.nch, ncell);
     TRON_CUDA(cudaGetLastError());
-    const long long nwork = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 7) / 8);
+    /* spokes in pairs when consecutive spokes are neighbours in angle (linear order) */
+    const int pair_env = getenv("TRON_DEGRID_PAIR") ? atoi(getenv("TRON_DEGRID_PAIR")) : -1;
+    const bool pair = pair_env >= 0 ? pair_env != 0 : d.pair_spokes != 0;
+    const int P = pair ? 2 : 1;
+    const long long nwork = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 8 * P - 1) / (8 * P));
     int bx = (int)(nwork < 148 * 32 ? nwork : 148 * 32);
     if (d.nch == 8) {
-        if (d.half_out) degrid_wide_kernel<1, true, 8><<<bx, 256, 0, s>>>(d, scratch);
-        else            degrid_wide_kernel<1, false, 8><<<bx, 256, 0, s>>>(d, scratch);
+        if (pair) launch_dw<1, 8, 2>(d, scratch, dim3(bx), s); else launch_dw<1, 8, 1>(d, scratch, dim3(bx), s);
     } else if (d.nch == 16) {
-        if (d.half_out) degrid_wide_kernel<1, true, 16><<<bx, 256, 0, s>>>(d, scratch);
-        else            degrid_wide_kernel<1, false, 16><<<bx, 256, 0, s>>>(d, scratch);
-    } else if (d.nch % 64 == 0) {
+        if (pair) launch_dw<1, 16, 2>(d, scratch, dim3(bx), s); else launch_dw<1, 16, 1>(d, scratch, dim3(bx), s);
+    } else if (d.nch % 64 == 0 && d.nc_total % 2 == 0 && d.ch0 % 2 == 0 && ((uintptr_t)d.samples) % 16 == 0) {
+        /* two adjacent channels per lane: the 8- / 16-byte sample stores need even channel offsets */
         dim3 grid(bx, d.nch / 64);
-        if (d.half_out) degrid_wide_kernel<2, true, 32><<<grid, 256, 0, s>>>(d, scratch);
-        else            degrid_wide_kernel<2, false, 32><<<grid, 256, 0, s>>>(d, scratch);
+        if (pair) launch_dw<2, 32, 2>(d, scratch, grid, s); else launch_dw<2, 32, 1>(d, scratch, grid, s);
     } else {
         dim3 grid(bx, d.nch / 32);
-        if (d.half_out) degrid_wide_kernel<1, true, 32><<<grid, 256, 0, s>>>(d, scratch);
-        else            degrid_wide_kernel<1, false, 32><<<grid, 256, 0, s>>>(d, scratch);
+        if (pair) launch_dw<1, 32, 2>(d, scratch, grid, s); else launch_dw<1, 32, 1>(d, scratch, grid, s);
     }
     TRON_CUDA(cudaGetLastError());
     return 0;

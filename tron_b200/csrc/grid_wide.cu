@@ -23,6 +23,7 @@
  * whole 32-byte sectors (4 cells of a row) of its channel plane.
  */
 #include "tron_internal.h"
+#include <stdlib.h>
 
 namespace tronb {
 
@@ -48,30 +49,44 @@ __device__ __forceinline__ void ffma2w(float2 &acc, float w, float2 v)
     acc = *reinterpret_cast<float2 *>(&a);
 }
 
-template <bool HALF>
-__device__ __forceinline__ float2 load_chan(const void *base, size_t idx)
+/* the NCHUNK adjacent channels a lane holds of one sample: ONE request of 4 .. 16 bytes */
+template <int NCHUNK, bool HALF>
+__device__ __forceinline__ void load_lane(float2 (&x)[NCHUNK], const char *p)
 {
     if (HALF) {
-        unsigned raw;
-        asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(raw) : "l"((const unsigned *)base + idx));
-        return __half22float2(*reinterpret_cast<__half2 *>(&raw));
+        if (NCHUNK == 2) {
+            unsigned r0, r1;
+            asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "l"(p));
+            x[0] = __half22float2(*reinterpret_cast<__half2 *>(&r0));
+            x[NCHUNK - 1] = __half22float2(*reinterpret_cast<__half2 *>(&r1));
+        } else {
+            unsigned raw;
+            asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(raw) : "l"(p));
+            x[0] = __half22float2(*reinterpret_cast<__half2 *>(&raw));
+        }
+    } else {
+        if (NCHUNK == 2)
+            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[0].x), "=f"(x[0].y), "=f"(x[NCHUNK - 1].x), "=f"(x[NCHUNK - 1].y) : "l"(p));
+        else
+            asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(x[0].x), "=f"(x[0].y) : "l"(p));
     }
-    float2 v;
-    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"((const float2 *)base + idx));
-    return v;
 }
 
 /* phase B: consume the list.  LPC = lanes per entry (32, or 16: two entries per step).
  * The list is first padded to a whole number of steps with zero-weight copies of its last entry
  * (same sample, so no new address is touched), which keeps the loop body free of branches;
- * DEPTH steps are in flight: offsets first, then the sample loads, then the FMAs. */
+ * DEPTH steps are in flight: offsets first, then the sample loads, then the FMAs.
+ * `lbase` = the lane's first channel of the group's first sample; a sample's address is one
+ * IMAD.WIDE (element offset x element size + lane base). */
 template <int LPC, int NCHUNK, int GS, bool HALF>
 __device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], WideList &L, int cnt,
-                                           const void *samples, int lane, int nvalid)
+                                           const char *lbase, int lane)
 {
     constexpr int EPI = 32 / LPC;                    /* entries per step */
     constexpr int DEPTH = NCHUNK == 1 ? 8 : 4;
     constexpr int STEP = DEPTH * EPI;
+    constexpr unsigned ROWB = HALF ? 4u : 8u;       /* bytes per channel */
     if (cnt == 0) return;
     const int padded = ((cnt + STEP - 1) / STEP) * STEP;     /* <= WCAP: WCAP is a multiple of STEP */
     if (cnt + lane < padded) {
@@ -82,15 +97,21 @@ __device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], WideLis
     }
     __syncwarp();
     const int sub = lane / LPC;
-    const int ch = min(lane % LPC, nvalid - 1);      /* lanes past the last channel recompute it; never stored */
     for (int e0 = 0; e0 < padded; e0 += STEP) {
         float2 x[DEPTH][NCHUNK];
+        if (EPI == 1) {                              /* the step's offsets: 16-byte shared loads */
 #pragma unroll
-        for (int d = 0; d < DEPTH; ++d) {
-            const unsigned off = L.off[e0 + d * EPI + sub];
+            for (int d = 0; d < DEPTH; d += 4) {
+                const uint4 o4 = *reinterpret_cast<const uint4 *>(&L.off[e0 + d]);
+                load_lane<NCHUNK, HALF>(x[d + 0], lbase + (unsigned long long)o4.x * ROWB);
+                load_lane<NCHUNK, HALF>(x[d + 1], lbase + (unsigned long long)o4.y * ROWB);
+                load_lane<NCHUNK, HALF>(x[d + 2], lbase + (unsigned long long)o4.z * ROWB);
+                load_lane<NCHUNK, HALF>(x[d + 3], lbase + (unsigned long long)o4.w * ROWB);
+            }
+        } else {
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c)
-                x[d][c] = load_chan<HALF>(samples, (size_t)off + min(c * 32 + ch, nvalid - 1));
+            for (int d = 0; d < DEPTH; ++d)
+                load_lane<NCHUNK, HALF>(x[d], lbase + (unsigned long long)L.off[e0 + d * EPI + sub] * ROWB);
         }
 #pragma unroll
         for (int d = 0; d < DEPTH; ++d) {
@@ -138,8 +159,17 @@ grid_wide_kernel(const GridLaunch g)
     const int *tpe = g.tab_pe + (size_t)tabi * g.npe;
     const int *lut = g.lut + (size_t)tabi * (g.nbins + 1);
     const size_t esz = HALF ? sizeof(__half2) : sizeof(float2);
-    const char *samples = (const char *)g.samples
+    /* lanes = channels: NCHUNK = 2 gives a lane the ADJACENT channels 2l, 2l + 1 (one request per sample); lanes past
+     * the last channel of a partial chunk recompute the last one and never store */
+    const int nvalid = g.nch - chan0;
+    const int chl = NCHUNK == 2 ? 2 * lane : min(lane % LPC, nvalid - 1);
+    const char *lbase = (const char *)g.samples
+        + ((size_t)ug * GS * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chan0 + chl)) * esz;
+    const char *pbase = (const char *)g.samples
         + ((size_t)ug * GS * g.slide * g.nro * g.nc_total + (size_t)(g.ch0 + chan0)) * esz;
+    /* opaque to the compiler: otherwise it keeps the kernel argument in a uniform register and adds it with two more
+     * instructions per sample address */
+    asm volatile("mov.b64 %0, %0;" : "+l"(lbase));
 
     const float W = g.kb.W;
     const bool same = g.nro == g.n;
@@ -241,17 +271,26 @@ grid_wide_kernel(const GridLaunch g)
                     bool any = false;
                     if (f < total) {
                         float wx[4], wy[2];
+                        float dxs[4], dys[2];
 #pragma unroll
-                        for (int cx = 0; cx < 4; ++cx) {
-                            const float dx = fma_ftz(ct, rf, -(float)(X0 + cx));        /* tron.cu:514 as compiled */
-                            wx[cx] = fabsf(dx) < W ? kb_weight(dx, g.kb) : 0.f;
-                        }
+                        for (int cx = 0; cx < 4; ++cx) dxs[cx] = fma_ftz(ct, rf, -(float)(X0 + cx));   /* tron.cu:514 as compiled */
+#pragma unroll
+                        for (int cy = 0; cy < 2; ++cy) dys[cy] = fma_ftz(st, rf, -(float)(Y0 + cy));
                         float fs = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);          /* tron.cu:412 */
                         if (r == 0) fs += fs;                                            /* r = 0 visited twice */
+                        if (g.kb.fast) {
+                            /* fitted polynomial: three packed Horner chains serve the six factors (the same FP32
+                             * operations per factor as kb_weight, so the weights are bit-identical) */
+                            const float2 a = kb_poly_pair(dxs[0], dxs[1], g.kb), b = kb_poly_pair(dxs[2], dxs[3], g.kb);
+                            const float2 c = kb_poly_pair(dys[0], dys[1], g.kb);
+                            wx[0] = fabsf(dxs[0]) < W ? a.x : 0.f; wx[1] = fabsf(dxs[1]) < W ? a.y : 0.f;
+                            wx[2] = fabsf(dxs[2]) < W ? b.x : 0.f; wx[3] = fabsf(dxs[3]) < W ? b.y : 0.f;
+                            wy[0] = fabsf(dys[0]) < W ? c.x * fs : 0.f; wy[1] = fabsf(dys[1]) < W ? c.y * fs : 0.f;
+                        } else {
 #pragma unroll
-                        for (int cy = 0; cy < 2; ++cy) {
-                            const float dy = fma_ftz(st, rf, -(float)(Y0 + cy));
-                            wy[cy] = fabsf(dy) < W ? kb_weight(dy, g.kb) * fs : 0.f;
+                            for (int cx = 0; cx < 4; ++cx) wx[cx] = fabsf(dxs[cx]) < W ? kb_weight(dxs[cx], g.kb) : 0.f;
+#pragma unroll
+                            for (int cy = 0; cy < 2; ++cy) wy[cy] = fabsf(dys[cy]) < W ? kb_weight(dys[cy], g.kb) * fs : 0.f;
                         }
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -266,17 +305,28 @@ grid_wide_kernel(const GridLaunch g)
                         const int slot = cnt + __popc(hit & ((1u << lane) - 1u));
                         L.wa[slot] = make_float4(w8[0], w8[1], w8[2], w8[3]);
                         L.wb[slot] = make_float4(w8[4], w8[5], w8[6], w8[7]);
-                        L.off[slot] = (unsigned)(((pmo & 0xffffff) * g.nro + g.nro / 2 + ridx)) * (unsigned)g.nc_total;
+                        const unsigned off = (unsigned)(((pmo & 0xffffff) * g.nro + g.nro / 2 + ridx)) * (unsigned)g.nc_total;
+                        L.off[slot] = off;
                         L.mask[slot] = pmo >> 24;
+                        /* the drain comes up to WCAP entries later: start the sample's lines towards L2 / L1 now (one
+                         * warp instruction covers 32 samples), so that its loads do not wait for DRAM */
+                        if (g.wide_prefetch) {
+                            const char *pf = pbase + (unsigned long long)off * (HALF ? 4u : 8u);
+#pragma unroll
+                            for (int b = 0; b < LPC * NCHUNK * (HALF ? 4 : 8); b += 128) {
+                                if (g.wide_prefetch == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(pf + b));
+                                else asm volatile("prefetch.global.L2 [%0];" :: "l"(pf + b));
+                            }
+                        }
                     }
                     cnt += __popc(hit);
                     if (cnt + 32 > WCAP) {                       /* phase B: lanes = channels */
-                        wide_drain<LPC, NCHUNK, GS, HALF>(acc, L, cnt, samples, lane, g.nch - chan0);
+                        wide_drain<LPC, NCHUNK, GS, HALF>(acc, L, cnt, lbase, lane);
                         cnt = 0;
                     }
                 }
             }
-            wide_drain<LPC, NCHUNK, GS, HALF>(acc, L, cnt, samples, lane, g.nch - chan0);
+            wide_drain<LPC, NCHUNK, GS, HALF>(acc, L, cnt, lbase, lane);
         }
 
         /* fold the two half-warps (nc = 16 mode), then every lane writes its channel plane */
@@ -298,7 +348,7 @@ grid_wide_kernel(const GridLaunch g)
                 if (zl < 0 || zl >= g.nslices) continue;
 #pragma unroll
                 for (int c = 0; c < NCHUNK; ++c) {
-                    const int ch = chan0 + c * 32 + lane;
+                    const int ch = NCHUNK == 2 ? chan0 + 2 * lane + c : chan0 + lane;
                     if (ch >= g.nch) continue;
                     float2 *out = g.grid + ((size_t)zl * g.nch + ch) * plane + (size_t)y0 * n + x0;
 #pragma unroll
@@ -342,15 +392,21 @@ bool grid_wide_applicable(const GridLaunch &g)
     return true;
 }
 
-int launch_grid_wide(const GridLaunch &g, cudaStream_t s)
+int launch_grid_wide(const GridLaunch &g_in, cudaStream_t s)
 {
-    if (g.nslices <= 0 || g.nch <= 0) return 0;
+    if (g_in.nslices <= 0 || g_in.nch <= 0) return 0;
+    GridLaunch g = g_in;
+    static const int pf = getenv("TRON_WIDE_PREFETCH") ? atoi(getenv("TRON_WIDE_PREFETCH")) : 2;
+    g.wide_prefetch = pf;
     if (g.gs == 4) {
         if (g.nch == 16) return launch_wide<16, 1, 4>(g, s);
         return launch_wide<32, 1, 4>(g, s);              /* 32 channels per CTA row */
     }
     if (g.nch == 16) return launch_wide<16, 1, 1>(g, s);
-    if (g.nch % 64 == 0) return launch_wide<32, 2, 1>(g, s);
+    /* two adjacent channels per lane: the 8- / 16-byte sample loads need even channel offsets */
+    const size_t esz = g.half_in ? 4 : 8;
+    if (g.nch % 64 == 0 && g.nc_total % 2 == 0 && g.ch0 % 2 == 0 && ((uintptr_t)g.samples) % (2 * esz) == 0)
+        return launch_wide<32, 2, 1>(g, s);
     return launch_wide<32, 1, 1>(g, s);
 }
 

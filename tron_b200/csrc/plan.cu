@@ -649,6 +649,7 @@ static int run_forward(tron_plan *p, void *d_out, const void *d_in, cudaStream_t
     d.n = g.nxos; d.nro = g.nro; d.npe = g.npe1work;
     d.nc_total = g.nc * g.nt; d.ch0 = g.coil_begin; d.nch = p->nch;
     d.kb = p->kb; d.half_out = p->cfg.half_out;
+    d.pair_spokes = !p->cfg.golden_angle;
     rc = run_degrid(p, d, s);
     p->last_launches += 3;
     return rc;

@@ -85,6 +85,7 @@ struct GridLaunch {               /* everything the gridding kernel needs */
     const int *tile_sched8 = nullptr;  /* grid_tile.cu: tile schedule, the n_near8 tiles next to DC first */
     int n_near8 = 0;
     const ScatterPlan *scat = nullptr; /* grid_scatter.cu (host pointer; the launcher passes the struct by value) */
+    int wide_prefetch = 0;        /* grid_wide.cu: 0 none, 1 L1, 2 L2 prefetch of a sample when its list entry is written */
     int zero_r2;                  /* cells with X^2 + Y^2 > zero_r2 can hold no sample and are NOT stored (the FFT pass
                                      that follows does not fetch them); INT_MAX: every cell is stored */
 };
@@ -98,6 +99,7 @@ struct DegridLaunch {
     int half_out;
     int nimg = 1;                 /* grids per launch: samples [nimg][npe][nro][nc_total], grid [nimg][nch][n][n] */
     int cs_stride = 0;            /* entries between the spoke tables of consecutive grids (0: shared) */
+    int pair_spokes = 0;          /* degrid_wide.cu: spokes pe, pe + 1 are neighbours in angle (linear order): one warp takes both */
 };
 
 int launch_grid(const GridLaunch &g, cudaStream_t s);
