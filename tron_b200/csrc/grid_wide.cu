@@ -176,20 +176,22 @@ grid_wide_kernel(const GridLaunch g)
     const float Rmaxf = (float)(n / 2 - 1);
     const float lut_scale = (float)g.nbins / PI_F;
 
-    for (int bi = quarter * 8 + warp; bi < quarter * 8 + 8; bi += 8) {
+    {
+        const int bi = quarter * 8 + warp;
         const int x0 = tx * 16 + (bi & 3) * 4, y0 = ty * 16 + (bi >> 2) * 2;
-        if (x0 >= n || y0 >= n) continue;
+        const bool inside = x0 < n && y0 < n;                 /* (n not a multiple of 16: blocks past the edge idle) */
         const int X0 = x0 - n / 2, Y0 = y0 - n / 2;
 
         /* annulus of the 8 cells (cell c = cy*4 + cx), broadcast from lanes 0..7 */
         int myband = 0;
-        if (lane < 8) myband = __ldg(g.cells + (size_t)(y0 + (lane >> 2)) * n + x0 + (lane & 3)).x;
+        if (lane < 8 && inside) myband = __ldg(g.cells + (size_t)(y0 + (lane >> 2)) * n + x0 + (lane & 3)).x;
         int band[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) band[c] = __shfl_sync(0xffffffffu, myband, c);
         bool dead = true;
 #pragma unroll
         for (int c = 0; c < 8; ++c) dead = dead && ((band[c] & 0xffff) > (band[c] >> 16));
+        dead = dead || !inside;
 
         float2 acc[NCHUNK][GS][8];
 #pragma unroll
@@ -339,26 +341,42 @@ grid_wide_kernel(const GridLaunch g)
                     acc[0][s][i].y += __shfl_down_sync(0xffffffffu, acc[0][s][i].y, 16);
                 }
         }
-        if (lane < LPC) {
-            const size_t plane = (size_t)n * n;
-            const int zg = ug * GS;
+        /* Store.  A lane holds ONE channel of the warp's 4 x 2 cells: written from here, every lane of a store would
+         * touch its own 128-byte line (ncu: half of the kernel's L1 tag requests were these stores).  The CTA's 8
+         * blocks tile 16 x 4 cells, so they are transposed through shared memory (the lists are no longer needed):
+         * per channel the tile is 4 rows of 128 contiguous bytes, one 16-byte store per lane. */
+        constexpr int CSTR = 66;                          /* float2 per channel: 64 cells + 16 bytes (bank groups) */
+        float2 *stage = reinterpret_cast<float2 *>(lists);
+        static_assert(sizeof(lists) >= (size_t)LPC * CSTR * sizeof(float2), "staging tile does not fit the lists");
+        const size_t plane = (size_t)n * n;
+        const int zg = ug * GS;
+        const int xb = tx * 16, yb = ty * 16 + quarter * 4;
+        const int brow = ((bi >> 2) & 1) * 2, bcol = (bi & 3) * 4;
+        __syncthreads();                                  /* every warp has drained its last list */
 #pragma unroll
-            for (int s = 0; s < GS; ++s) {
-                const int zl = zg + s - g.z0;
-                if (zl < 0 || zl >= g.nslices) continue;
+        for (int s = 0; s < GS; ++s) {
+            const int zl = zg + s - g.z0;
+            if (zl < 0 || zl >= g.nslices) continue;      /* (uniform over the CTA) */
 #pragma unroll
-                for (int c = 0; c < NCHUNK; ++c) {
-                    const int ch = NCHUNK == 2 ? chan0 + 2 * lane + c : chan0 + lane;
-                    if (ch >= g.nch) continue;
-                    float2 *out = g.grid + ((size_t)zl * g.nch + ch) * plane + (size_t)y0 * n + x0;
+            for (int c = 0; c < NCHUNK; ++c) {
+                if (lane < LPC) {
 #pragma unroll
                     for (int cy = 0; cy < 2; ++cy) {
-                        float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)cy * n);
+                        float4 *o4 = reinterpret_cast<float4 *>(stage + lane * CSTR + (brow + cy) * 16 + bcol);
                         const float2 *a = &acc[c][s][cy * 4];
                         o4[0] = make_float4(a[0].x * g.scale, a[0].y * g.scale, a[1].x * g.scale, a[1].y * g.scale);
                         o4[1] = make_float4(a[2].x * g.scale, a[2].y * g.scale, a[3].x * g.scale, a[3].y * g.scale);
                     }
                 }
+                __syncthreads();
+                const int row = lane >> 3, col = (lane & 7) * 2;
+                for (int chl = warp; chl < LPC; chl += 8) {
+                    const int ch = NCHUNK == 2 ? chan0 + 2 * chl + c : chan0 + chl;
+                    if (ch >= g.nch || yb + row >= n || xb + col >= n) continue;
+                    const float4 v = *reinterpret_cast<const float4 *>(stage + chl * CSTR + row * 16 + col);
+                    *reinterpret_cast<float4 *>(g.grid + ((size_t)zl * g.nch + ch) * plane + (size_t)(yb + row) * n + xb + col) = v;
+                }
+                __syncthreads();
             }
         }
     }
