@@ -531,10 +531,32 @@ class Cfg5Pair:
                 "gpu_launches_per_step": self.fw.last_launches() + self.ad.last_launches() + 1 + (1 if world > 1 else 0),
                 "e2e": {"value": self.nsamp / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": gf["in_elems"] * 4, "d2h_bytes_per_step": self.npix * 8},
-                "roofline": {"bound": "hbm (secondary: fp32, 36 flop/B at W = 6, SURVEY 8d)", "kernel": "degrid_wide + grid_wide (the two interpolation kernels' algorithmic bytes over the whole pair's time)",
-                             "achieved": 2 * b_dir / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": 2 * b_dir / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": 2 * b_dir}}
+                "roofline": self.fp32_roofline(ms, b_dir, peak, peak_src)}
+
+    def fp32_roofline(self, ms, b_dir, hbm_peak, hbm_src):
+        """cfg5 is FP32 bound (36 flop/B at W = 6).  Useful arithmetic: one complex x real FMA = 4 flop per
+        tap and channel; the forward transform has (2W)^2 = 144 taps per sample, the adjoint 0.943 of that (the
+        reference's annulus drops the corners of the square support).  Peak = the FFMA2 rate measured on this pool's
+        B200 by profiles/ffma2_bench.cu (profiles/fp32_peak.json), else 148 SMs x 128 lanes x 2 x 1.965 GHz."""
+        gf, ncl = self.gf, self.ncl
+        nsamp = gf["nro"] * gf["npe1work"]
+        taps = 144.0
+        flops = 4.0 * ncl * nsamp * taps * (1.0 + 0.943)
+        peak, src = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal (148 SMs x 128 FP32 lanes x 2 x 1.965 GHz)"
+        pj = os.path.join(ROOT, "profiles", "fp32_peak.json")
+        if os.path.isfile(pj):
+            try:
+                j = json.load(open(pj))
+                peak, src = float(j["ffma2_tflops"]), j.get("source", "profiles/fp32_peak.json")
+            except Exception:
+                pass
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"bound": "fp32", "kernel": "degrid_wide + grid_wide: useful interpolation flops of both directions over the WHOLE pair's time (FFT passes included)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src,
+                "algorithmic_flops_per_step": flops,
+                "hbm": {"achieved": 2 * b_dir / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": 2 * b_dir / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                        "algorithmic_bytes_per_step": 2 * b_dir}}
 
     def image(self):
         self.step(False)
