@@ -33,7 +33,7 @@ namespace tronb {
 struct __align__(16) WideList {
     float4 wa[WCAP];                  /* weights of cells (0..3, row 0) */
     float4 wb[WCAP];                  /* weights of cells (0..3, row 1) */
-    unsigned off[WCAP];               /* sample offset in elements from the group's channel base (launch checks it fits 32 bits) */
+    unsigned off[WCAP + 8];           /* sample offset in elements from the group's channel base (launch checks it fits 32 bits) */
     int mask[WCAP];                   /* slices of the group whose window holds the spoke */
 };
 
@@ -49,95 +49,142 @@ __device__ __forceinline__ void ffma2w(float2 &acc, float w, float2 v)
     acc = *reinterpret_cast<float2 *>(&a);
 }
 
-/* the NCHUNK adjacent channels a lane holds of one sample: ONE request of 4 .. 16 bytes */
+/* the NCHUNK adjacent channels a lane holds of one sample: ONE request of 4 .. 16 bytes, kept as loaded (half
+ * pairs stay packed until they are used: a step in flight costs one register per channel) */
+template <int NCHUNK, bool HALF> struct LaneRaw { unsigned long long q[HALF ? (NCHUNK + 1) / 2 : NCHUNK]; };
+
 template <int NCHUNK, bool HALF>
-__device__ __forceinline__ void load_lane(float2 (&x)[NCHUNK], const char *p)
+__device__ __forceinline__ void load_lane(LaneRaw<NCHUNK, HALF> &x, const char *p)
 {
     if (HALF) {
         if (NCHUNK == 2) {
-            unsigned r0, r1;
-            asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "l"(p));
-            x[0] = __half22float2(*reinterpret_cast<__half2 *>(&r0));
-            x[NCHUNK - 1] = __half22float2(*reinterpret_cast<__half2 *>(&r1));
+            asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(x.q[0]) : "l"(p));
         } else {
             unsigned raw;
             asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(raw) : "l"(p));
-            x[0] = __half22float2(*reinterpret_cast<__half2 *>(&raw));
+            x.q[0] = raw;
         }
     } else {
         if (NCHUNK == 2)
-            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(x[0].x), "=f"(x[0].y), "=f"(x[NCHUNK - 1].x), "=f"(x[NCHUNK - 1].y) : "l"(p));
+            asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(x.q[0]), "=l"(x.q[NCHUNK - 1]) : "l"(p));
         else
-            asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(x[0].x), "=f"(x[0].y) : "l"(p));
+            asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(x.q[0]) : "l"(p));
+    }
+}
+
+template <int NCHUNK, bool HALF>
+__device__ __forceinline__ float2 lane_value(const LaneRaw<NCHUNK, HALF> &x, int c)
+{
+    if (HALF) {
+        const unsigned raw = (unsigned)(c ? (x.q[0] >> 32) : x.q[0]);
+        return __half22float2(*reinterpret_cast<const __half2 *>(&raw));
+    }
+    return *reinterpret_cast<const float2 *>(&x.q[c]);
+}
+
+/* the sample loads of DEPTH list steps */
+template <int LPC, int NCHUNK, bool HALF, int DEPTH>
+__device__ __forceinline__ void drain_load(LaneRaw<NCHUNK, HALF> (&x)[DEPTH], const WideList &L, int e0, const char *lbase, int sub)
+{
+    constexpr int EPI = 32 / LPC;
+    constexpr unsigned ROWB = HALF ? 4u : 8u;       /* bytes per channel */
+    if (EPI == 1 && DEPTH % 4 == 0) {                /* the step's offsets: 16-byte shared loads */
+#pragma unroll
+        for (int d = 0; d < DEPTH; d += 4) {
+            const uint4 o4 = *reinterpret_cast<const uint4 *>(&L.off[e0 + d]);
+            load_lane<NCHUNK, HALF>(x[d + 0], lbase + (unsigned long long)o4.x * ROWB);
+            load_lane<NCHUNK, HALF>(x[d + 1], lbase + (unsigned long long)o4.y * ROWB);
+            load_lane<NCHUNK, HALF>(x[d + 2], lbase + (unsigned long long)o4.z * ROWB);
+            load_lane<NCHUNK, HALF>(x[d + 3], lbase + (unsigned long long)o4.w * ROWB);
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+            load_lane<NCHUNK, HALF>(x[d], lbase + (unsigned long long)L.off[e0 + d * EPI + sub] * ROWB);
+    }
+}
+
+template <int LPC, int NCHUNK, int GS, bool HALF, int DEPTH>
+__device__ __forceinline__ void drain_fma(float2 (&acc)[NCHUNK][GS][8], const LaneRaw<NCHUNK, HALF> (&x)[DEPTH], const WideList &L,
+                                          int e0, int sub)
+{
+    constexpr int EPI = 32 / LPC;
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+        const int e = e0 + d * EPI + sub;
+        const float4 p = L.wa[e], q = L.wb[e];
+        const int m = GS > 1 ? L.mask[e] : 1;
+        float2 v[NCHUNK];
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) v[c] = lane_value<NCHUNK, HALF>(x[d], c);
+#pragma unroll
+        for (int s = 0; s < GS; ++s)
+            if (GS == 1 || (m >> s) & 1) {
+#pragma unroll
+                for (int c = 0; c < NCHUNK; ++c) {
+                    ffma2w(acc[c][s][0], p.x, v[c]); ffma2w(acc[c][s][1], p.y, v[c]);
+                    ffma2w(acc[c][s][2], p.z, v[c]); ffma2w(acc[c][s][3], p.w, v[c]);
+                    ffma2w(acc[c][s][4], q.x, v[c]); ffma2w(acc[c][s][5], q.y, v[c]);
+                    ffma2w(acc[c][s][6], q.z, v[c]); ffma2w(acc[c][s][7], q.w, v[c]);
+                }
+            }
     }
 }
 
 /* phase B: consume the list.  LPC = lanes per entry (32, or 16: two entries per step).
  * The list is first padded to a whole number of steps with zero-weight copies of its last entry
- * (same sample, so no new address is touched), which keeps the loop body free of branches;
- * DEPTH steps are in flight: offsets first, then the sample loads, then the FMAs.
+ * (same sample, so no new address is touched), which keeps the loop body free of branches.
+ * Two buffers of DEPTH steps alternate: the loads of the next DEPTH steps are issued before the FMAs of the
+ * current ones, so a warp always has sample loads in flight (ncu: a quarter of the stall samples sat on the
+ * first use of a step's samples when loads and FMAs took turns).
  * `lbase` = the lane's first channel of the group's first sample; a sample's address is one
  * IMAD.WIDE (element offset x element size + lane base). */
-template <int LPC, int NCHUNK, int GS, bool HALF>
+template <int LPC, int NCHUNK, int GS, bool HALF, bool PIPE>
 __device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], WideList &L, int cnt,
                                            const char *lbase, int lane)
 {
     constexpr int EPI = 32 / LPC;                    /* entries per step */
-    constexpr int DEPTH = NCHUNK == 1 ? 8 : 4;
-    constexpr int STEP = DEPTH * EPI;
-    constexpr unsigned ROWB = HALF ? 4u : 8u;       /* bytes per channel */
+    /* one channel chunk (64-register instantiations, cfg3): the second buffer would spill -- 8 steps at a time, loads
+     * then FMAs (measured: 2.91 vs 3.12 ms per 32 cfg3 slices) */
+    constexpr int DEPTH = !PIPE ? 8 / EPI : ((HALF || NCHUNK == 1) ? 4 : 2);
+    constexpr int STEP = DEPTH * EPI;                /* <= 8 */
     if (cnt == 0) return;
     const int padded = ((cnt + STEP - 1) / STEP) * STEP;     /* <= WCAP: WCAP is a multiple of STEP */
-    if (cnt + lane < padded) {
-        L.wa[cnt + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        L.wb[cnt + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cnt + lane < padded + STEP) {                /* (offsets one step further: the loads run one step ahead) */
+        if (cnt + lane < padded) {
+            L.wa[cnt + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            L.wb[cnt + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            L.mask[cnt + lane] = 0;
+        }
         L.off[cnt + lane] = L.off[cnt - 1];
-        L.mask[cnt + lane] = 0;
     }
     __syncwarp();
     const int sub = lane / LPC;
-    for (int e0 = 0; e0 < padded; e0 += STEP) {
-        float2 x[DEPTH][NCHUNK];
-        if (EPI == 1) {                              /* the step's offsets: 16-byte shared loads */
-#pragma unroll
-            for (int d = 0; d < DEPTH; d += 4) {
-                const uint4 o4 = *reinterpret_cast<const uint4 *>(&L.off[e0 + d]);
-                load_lane<NCHUNK, HALF>(x[d + 0], lbase + (unsigned long long)o4.x * ROWB);
-                load_lane<NCHUNK, HALF>(x[d + 1], lbase + (unsigned long long)o4.y * ROWB);
-                load_lane<NCHUNK, HALF>(x[d + 2], lbase + (unsigned long long)o4.z * ROWB);
-                load_lane<NCHUNK, HALF>(x[d + 3], lbase + (unsigned long long)o4.w * ROWB);
-            }
-        } else {
-#pragma unroll
-            for (int d = 0; d < DEPTH; ++d)
-                load_lane<NCHUNK, HALF>(x[d], lbase + (unsigned long long)L.off[e0 + d * EPI + sub] * ROWB);
+    if (!PIPE) {
+        for (int e0 = 0; e0 < padded; e0 += STEP) {
+            LaneRaw<NCHUNK, HALF> x[DEPTH];
+            drain_load<LPC, NCHUNK, HALF, DEPTH>(x, L, e0, lbase, sub);
+            drain_fma<LPC, NCHUNK, GS, HALF, DEPTH>(acc, x, L, e0, sub);
         }
-#pragma unroll
-        for (int d = 0; d < DEPTH; ++d) {
-            const int e = e0 + d * EPI + sub;
-            const float4 p = L.wa[e], q = L.wb[e];
-            const int m = GS > 1 ? L.mask[e] : 1;
-#pragma unroll
-            for (int s = 0; s < GS; ++s)
-                if (GS == 1 || (m >> s) & 1) {
-#pragma unroll
-                    for (int c = 0; c < NCHUNK; ++c) {
-                        ffma2w(acc[c][s][0], p.x, x[d][c]); ffma2w(acc[c][s][1], p.y, x[d][c]);
-                        ffma2w(acc[c][s][2], p.z, x[d][c]); ffma2w(acc[c][s][3], p.w, x[d][c]);
-                        ffma2w(acc[c][s][4], q.x, x[d][c]); ffma2w(acc[c][s][5], q.y, x[d][c]);
-                        ffma2w(acc[c][s][6], q.z, x[d][c]); ffma2w(acc[c][s][7], q.w, x[d][c]);
-                    }
-                }
-        }
+        __syncwarp();
+        return;
+    }
+    LaneRaw<NCHUNK, HALF> xa[DEPTH], xb[DEPTH];
+    drain_load<LPC, NCHUNK, HALF, DEPTH>(xa, L, 0, lbase, sub);
+    for (int e0 = 0; e0 < padded; e0 += 2 * STEP) {
+        drain_load<LPC, NCHUNK, HALF, DEPTH>(xb, L, e0 + STEP, lbase, sub);
+        drain_fma<LPC, NCHUNK, GS, HALF, DEPTH>(acc, xa, L, e0, sub);
+        if (e0 + STEP >= padded) break;
+        drain_load<LPC, NCHUNK, HALF, DEPTH>(xa, L, min(e0 + 2 * STEP, padded), lbase, sub);
+        drain_fma<LPC, NCHUNK, GS, HALF, DEPTH>(acc, xb, L, e0 + STEP, sub);
     }
     __syncwarp();
 }
 
 /* one channel chunk, one slice per group (cfg3): 4 CTAs/SM (64 registers, 26 words of spill) measured 8 % faster
  * than 2 (128 registers); the wider instantiations spill too much below 128 registers (cfg5: 3 CTAs/SM 35 % slower) */
-template <int LPC, int NCHUNK, int GS, bool HALF>
-__global__ void __launch_bounds__(256, (NCHUNK == 1 && GS == 1) ? 4 : 2)
+template <int LPC, int NCHUNK, int GS, bool HALF, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 grid_wide_kernel(const GridLaunch g)
 {
     __shared__ WideList lists[8];
@@ -323,12 +370,12 @@ grid_wide_kernel(const GridLaunch g)
                     }
                     cnt += __popc(hit);
                     if (cnt + 32 > WCAP) {                       /* phase B: lanes = channels */
-                        wide_drain<LPC, NCHUNK, GS, HALF>(acc, L, cnt, lbase, lane);
+                        wide_drain<LPC, NCHUNK, GS, HALF, (NCHUNK == 2 || MINB == 3)>(acc, L, cnt, lbase, lane);
                         cnt = 0;
                     }
                 }
             }
-            wide_drain<LPC, NCHUNK, GS, HALF>(acc, L, cnt, lbase, lane);
+            wide_drain<LPC, NCHUNK, GS, HALF, (NCHUNK == 2 || MINB == 3)>(acc, L, cnt, lbase, lane);
         }
 
         /* fold the two half-warps (nc = 16 mode), then every lane writes its channel plane */
@@ -382,15 +429,15 @@ grid_wide_kernel(const GridLaunch g)
     }
 }
 
-template <int LPC, int NCHUNK, int GS>
+template <int LPC, int NCHUNK, int GS, int MINB = ((NCHUNK == 1 && GS == 1) ? 4 : 2)>
 static int launch_wide(GridLaunch g, cudaStream_t s)
 {
     int tiles = ((g.n + 15) / 16) * ((g.n + 15) / 16);
     g.ngroups = (g.z0 + g.nslices - 1) / GS - g.z0 / GS + 1;
     int per_cta = LPC * NCHUNK;
     dim3 grid(tiles * 4 * g.ngroups, (g.nch + per_cta - 1) / per_cta);
-    if (g.half_in) grid_wide_kernel<LPC, NCHUNK, GS, true><<<grid, 256, 0, s>>>(g);
-    else           grid_wide_kernel<LPC, NCHUNK, GS, false><<<grid, 256, 0, s>>>(g);
+    if (g.half_in) grid_wide_kernel<LPC, NCHUNK, GS, true, MINB><<<grid, 256, 0, s>>>(g);
+    else           grid_wide_kernel<LPC, NCHUNK, GS, false, MINB><<<grid, 256, 0, s>>>(g);
     TRON_CUDA(cudaGetLastError());
     return 0;
 }
@@ -421,6 +468,7 @@ int launch_grid_wide(const GridLaunch &g_in, cudaStream_t s)
         return launch_wide<32, 1, 4>(g, s);              /* 32 channels per CTA row */
     }
     if (g.nch == 16) return launch_wide<16, 1, 1>(g, s);
+    /* (32 channels at 3 blocks per SM, 80 registers, pipelined drain: 3.27 vs 2.93 ms per 32 cfg3 slices -- 4 blocks stay) */
     /* two adjacent channels per lane: the 8- / 16-byte sample loads need even channel offsets */
     const size_t esz = g.half_in ? 4 : 8;
     if (g.nch % 64 == 0 && g.nc_total % 2 == 0 && g.ch0 % 2 == 0 && ((uintptr_t)g.samples) % (2 * esz) == 0)
