@@ -594,6 +594,8 @@ def test_full_size_linearity_and_shard_consistency(lib):
     (32, dict(adjoint=True, golden=True, undersamp=0.25, prof_slide=3, skip_angles=9)),
     (16, dict(adjoint=True, golden=True, kernwidth=6.0)),                        # cfg5 shard on 4 GPUs: wide kernel for 16 coils
     (16, dict(adjoint=True, kernwidth=3.5, undersamp=0.5, prof_slide=20)),
+    (8, dict(adjoint=True, kernwidth=6.0)),                                      # cfg5 shard on 8 GPUs: four entries per step
+    (8, dict(adjoint=True, golden=True, kernwidth=3.0, undersamp=0.5, prof_slide=7)),   # ... with 4-slice tap sharing
 ])
 def test_wide_channel_gridding_vs_reference(lib, reflib_wide, nc, flags):
     import tron_b200 as t

@@ -379,14 +379,16 @@ grid_wide_kernel(const GridLaunch g)
         }
 
         /* fold the two half-warps (nc = 16 mode), then every lane writes its channel plane */
-        if (LPC == 16) {
+        if (LPC < 32) {
 #pragma unroll
             for (int s = 0; s < GS; ++s)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    acc[0][s][i].x += __shfl_down_sync(0xffffffffu, acc[0][s][i].x, 16);
-                    acc[0][s][i].y += __shfl_down_sync(0xffffffffu, acc[0][s][i].y, 16);
-                }
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int o = 16; o >= LPC; o >>= 1) {
+                        acc[0][s][i].x += __shfl_down_sync(0xffffffffu, acc[0][s][i].x, o);
+                        acc[0][s][i].y += __shfl_down_sync(0xffffffffu, acc[0][s][i].y, o);
+                    }
         }
         /* Store.  A lane holds ONE channel of the warp's 4 x 2 cells: written from here, every lane of a store would
          * touch its own 128-byte line (ncu: half of the kernel's L1 tag requests were these stores).  The CTA's 8
@@ -447,7 +449,7 @@ bool grid_wide_applicable(const GridLaunch &g)
     /* nc = 16 is faster on the thread-per-cell kernel (measured: 9.3 vs 18.3 us/slice on cfg4) */
     /* ... for the default kernel width; with wide kernels (cfg5's 16-coil shards at -k 6) a sample serves dozens of
      * blocks and fetching it once per block wins again */
-    const bool few = g.nch == 16 && g.kb.W >= 3.f;
+    const bool few = (g.nch == 16 || (g.nch == 8 && getenv("TRON_NO_WIDE8") == nullptr)) && g.kb.W >= 3.f;
     if (!few && (g.nch < 32 || g.nch % 16 != 0)) return false;
     if (g.n % 4 != 0) return false;
     if (g.gs != 1 && g.gs != 4) return false;
@@ -465,9 +467,11 @@ int launch_grid_wide(const GridLaunch &g_in, cudaStream_t s)
     g.wide_prefetch = pf;
     if (g.gs == 4) {
         if (g.nch == 16) return launch_wide<16, 1, 4>(g, s);
+        if (g.nch == 8) return launch_wide<8, 1, 4>(g, s);
         return launch_wide<32, 1, 4>(g, s);              /* 32 channels per CTA row */
     }
     if (g.nch == 16) return launch_wide<16, 1, 1>(g, s);
+    if (g.nch == 8) return launch_wide<8, 1, 1>(g, s);           /* cfg5's shards on 8 GPUs: four list entries per step */
     /* (32 channels at 3 blocks per SM, 80 registers, pipelined drain: 3.27 vs 2.93 ms per 32 cfg3 slices -- 4 blocks stay) */
     /* two adjacent channels per lane: the 8- / 16-byte sample loads need even channel offsets */
     const size_t esz = g.half_in ? 4 : 8;
