@@ -163,6 +163,29 @@ def test_ra_header_layout_and_roundtrip(lib, tmp_path):
     assert 88 + 6 * 512 * 20271 * 8 == 498180184
 
 
+def test_ra_payload_beyond_2_gib(lib, tmp_path):
+    """A single read(2)/write(2) moves at most 0x7ffff000 bytes on Linux; the reference's loop loses the tail of larger
+    payloads (ra.cu:153-158).  2 GiB + 4 KiB through ra_write / ra_read: every chunk boundary and the tail."""
+    import shutil
+    import tron_b200 as t
+    if shutil.disk_usage(str(tmp_path)).free < 6 * (1 << 30):
+        pytest.skip("needs 6 GiB of scratch space")
+    n = (1 << 29) + 1024                                   # float32 elements: 2 GiB + 4 KiB
+    a = np.empty(n, dtype=np.float32)
+    a.view(np.uint32)[:] = np.arange(n, dtype=np.uint32)    # position-coded bit patterns
+    f = str(tmp_path / "big.ra")
+    t.ra_write(f, a, dims=[n], eltype=3)                   # ra.h:63-72: 3 = float
+    assert os.path.getsize(f) == 48 + 8 + 4 * n
+    b, dims, et, eb = t.ra_read(f)
+    assert dims == [n] and (et, eb) == (3, 4) and b.shape == a.shape
+    bu = b.view(np.uint32)
+    assert np.array_equal(bu[-4096:], np.arange(n - 4096, n, dtype=np.uint32))           # the tail
+    for edge in (0x7ffff000 // 4, (1 << 30) // 4, (1 << 31) // 4):                         # syscall cap, I/O chunks
+        assert np.array_equal(bu[edge - 8:edge + 8], np.arange(edge - 8, edge + 8, dtype=np.uint32))
+    assert np.array_equal(bu[::4099], np.arange(0, n, 4099, dtype=np.uint32))
+    os.remove(f)
+
+
 def test_ra_matches_oracle_writer(lib, oracle, tmp_path):
     """Bytes written by the product are bytes the oracle's reader understands, and vice versa."""
     import tron_b200 as t
