@@ -210,14 +210,18 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
                 const int u = isrow ? xlo + i : ylo + min(i - nux, nuy - 1);
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    float w4[DW_S];
+                    float w4[DW_S], dd[DW_S];
+#pragma unroll
+                    for (int k = 0; k < DW_S; ++k) dd[k] = (float)u - (isrow ? X[p * DW_S + k] : Y[p * DW_S + k]);
+                    /* two factors per packed evaluation (same FP32 operations as kb_weight); arguments outside the
+                     * support give garbage that the selects drop */
+                    const float2 k01 = kb_weight_pair(dd[0], dd[1], d.kb), k23 = kb_weight_pair(dd[2], dd[3], d.kb);
+                    const float kk[DW_S] = { k01.x, k01.y, k23.x, k23.y };
 #pragma unroll
                     for (int k = 0; k < DW_S; ++k) {
-                        const int s = p * DW_S + k;
-                        const float dd = (float)u - (isrow ? X[s] : Y[s]);
                         const bool live = (ro0 + k < d.nro) && (pe0 + p < d.npe) && (npass == 1 || p == pass)
-                            && fabsf(dd) < W && (isrow || i - nux < nuy);        /* tron.cu:343 via gridkernel */
-                        w4[k] = live ? kb_weight(dd, d.kb) : 0.f;
+                            && fabsf(dd[k]) < W && (isrow || i - nux < nuy);     /* tron.cu:343 via gridkernel */
+                        w4[k] = live ? kk[k] : 0.f;
                     }
                     /* the pad columns of the last quad repeat the last column with zero weights (no new address) */
                     if (isrow) S.wx[p][i] = make_float4(w4[0], w4[1], w4[2], w4[3]);

@@ -327,19 +327,15 @@ grid_wide_kernel(const GridLaunch g)
                         for (int cy = 0; cy < 2; ++cy) dys[cy] = fma_ftz(st, rf, -(float)(Y0 + cy));
                         float fs = fmaf(g.sdc_a, fabsf((float)ridx), g.sdc_b);          /* tron.cu:412 */
                         if (r == 0) fs += fs;                                            /* r = 0 visited twice */
-                        if (g.kb.fast) {
-                            /* fitted polynomial: three packed Horner chains serve the six factors (the same FP32
-                             * operations per factor as kb_weight, so the weights are bit-identical) */
-                            const float2 a = kb_poly_pair(dxs[0], dxs[1], g.kb), b = kb_poly_pair(dxs[2], dxs[3], g.kb);
-                            const float2 c = kb_poly_pair(dys[0], dys[1], g.kb);
+                        {
+                            /* three packed evaluations serve the six factors (the same FP32 operations per factor as
+                             * kb_weight -- fitted polynomial or rational form -- so the weights are bit-identical);
+                             * arguments outside the support give garbage that the selects drop */
+                            const float2 a = kb_weight_pair(dxs[0], dxs[1], g.kb), b = kb_weight_pair(dxs[2], dxs[3], g.kb);
+                            const float2 c = kb_weight_pair(dys[0], dys[1], g.kb);
                             wx[0] = fabsf(dxs[0]) < W ? a.x : 0.f; wx[1] = fabsf(dxs[1]) < W ? a.y : 0.f;
                             wx[2] = fabsf(dxs[2]) < W ? b.x : 0.f; wx[3] = fabsf(dxs[3]) < W ? b.y : 0.f;
                             wy[0] = fabsf(dys[0]) < W ? c.x * fs : 0.f; wy[1] = fabsf(dys[1]) < W ? c.y * fs : 0.f;
-                        } else {
-#pragma unroll
-                            for (int cx = 0; cx < 4; ++cx) wx[cx] = fabsf(dxs[cx]) < W ? kb_weight(dxs[cx], g.kb) : 0.f;
-#pragma unroll
-                            for (int cy = 0; cy < 2; ++cy) wy[cy] = fabsf(dys[cy]) < W ? kb_weight(dys[cy], g.kb) * fs : 0.f;
                         }
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
