@@ -360,6 +360,11 @@ fwd_pass_b_kernel(const float2 *__restrict__ tmp, float2 *__restrict__ grid, con
  */
 template <int N, int L> struct P2 {
     static constexpr int T = N / 8;                 /* threads per line */
+    /* exchange buffers per line.  Two alternate, one barrier per stage -- except for the longest lines, where two
+     * buffers of 4 lines fill the SM's shared memory with ONE block (32 of 64 warps; ncu on the 2048-point passes:
+     * every unit below 65 %, barrier and scoreboard stalls).  There a single buffer and a second barrier per stage
+     * let two blocks share an SM. */
+    static constexpr int NBUF = N >= 2048 ? 1 : 2;
     /* line pitch: >= phys(N-1)+1 and == 16/L (mod 16), so that the transposed read of the
      * store phase (L lines x 16/L consecutive outputs per half-warp) hits 16 distinct bank pairs */
     static constexpr int BASE = N + N / 16;
@@ -383,8 +388,20 @@ template <int N>
 __device__ __forceinline__ void p2_line_sync(int l)
 {
     constexpr int T = N / 8;
-    if (T >= 32) asm volatile("bar.sync %0, %1;" ::"r"(l + 1), "n"(T) : "memory");
-    else __syncthreads();
+    if (T >= 32) {
+        /* barrier ids as immediates (a line index is < 8 whenever T >= 32): with a register operand ptxas reserves
+         * all 16 named barriers for the block, which caps the blocks per SM */
+        switch (l) {
+        case 0: asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"n"(T) : "memory"); break;
+        case 3: asm volatile("bar.sync 4, %0;" ::"n"(T) : "memory"); break;
+        case 4: asm volatile("bar.sync 5, %0;" ::"n"(T) : "memory"); break;
+        case 5: asm volatile("bar.sync 6, %0;" ::"n"(T) : "memory"); break;
+        case 6: asm volatile("bar.sync 7, %0;" ::"n"(T) : "memory"); break;
+        default: asm volatile("bar.sync 8, %0;" ::"n"(T) : "memory"); break;
+        }
+    } else __syncthreads();
 }
 
 template <int N, int Ns, int R, int SGN>
@@ -421,7 +438,7 @@ __device__ __forceinline__ void p2_stage(float2 (&v)[8], float2 *dst, const floa
     }
 }
 
-template <int N, int Ns, int SGN>
+template <int N, int Ns, int SGN, bool SINGLE = (N >= 2048)>
 __device__ __forceinline__ void p2_stages(float2 (&v)[8], float2 *bufA, float2 *bufB, const float2 *stw, int j, int l)
 {
     constexpr int REM = N / Ns;
@@ -433,7 +450,8 @@ __device__ __forceinline__ void p2_stages(float2 (&v)[8], float2 *bufA, float2 *
         const float2 *s = bufA + phys(j);
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = s[p2_roff<T>(q)];
-        p2_stages<N, Ns * R, SGN>(v, bufB, bufA, stw, j, l);
+        if (SINGLE) p2_line_sync<N>(l);                   /* single buffer: everyone has read before the next stage writes */
+        p2_stages<N, Ns * R, SGN, SINGLE>(v, bufB, bufA, stw, j, l);
     } else {
         __syncthreads();                     /* the store phase reads every line of the CTA */
     }
@@ -444,21 +462,21 @@ template <int N> __host__ __device__ constexpr int p2_nstages() { int s = 0, m =
 
 /* Transform: registers in (element j + q*T of the line), result in shared memory, natural order.
  * Returns the line base inside the result buffer.  lineA/lineB are this line's two buffers. */
-template <int N, int SGN>
+template <int N, int SGN, bool SINGLE = (N >= 2048)>
 __device__ __forceinline__ float2 *p2_fft(float2 (&v)[8], float2 *lineA, float2 *lineB, const float2 *stw, int j, int l)
 {
-    p2_stages<N, 1, SGN>(v, lineA, lineB, stw, j, l);
+    p2_stages<N, 1, SGN, SINGLE>(v, lineA, lineB, stw, j, l);
     return (p2_nstages<N>() & 1) ? lineA : lineB;
 }
 
 template <int N, int L>
-__global__ void __launch_bounds__(L *(N / 8))
+__global__ void __launch_bounds__(L *(N / 8), (N >= 2048 && L * (N / 8) <= 1024 ? 2 : 1))
 p2_adj_pass_a(const float2 *__restrict__ grid, float2 *__restrict__ tmp, const float2 *__restrict__ tw, int nkeep,
               int zero_r2)
 {
     extern __shared__ float2 smem[];
     constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
-    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
+    float2 *bufA = smem, *bufB = smem + (P2<N, L>::NBUF - 1) * L * PITCH, *stw = smem + P2<N, L>::NBUF * L * PITCH;
     const int l = threadIdx.x / T, j = threadIdx.x % T;
     const int y0 = blockIdx.x * L;
     const size_t plane = blockIdx.y;
@@ -491,7 +509,7 @@ p2_adj_pass_b(const float2 *__restrict__ tmp, void *__restrict__ outv, const flo
 {
     extern __shared__ float2 smem[];
     constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
-    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
+    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;   /* two buffers: 64 registers hold one block per SM anyway */
     const int l = threadIdx.x / T, j = threadIdx.x % T;
     const int b0 = blockIdx.x * L;
     const int slice = blockIdx.y;
@@ -515,7 +533,7 @@ p2_adj_pass_b(const float2 *__restrict__ tmp, void *__restrict__ outv, const flo
             for (int q = 0; q < 8; ++q) nv[q] = line_ok ? src[(size_t)(ch + 1) * chan_stride + q * T] : make_float2(0.f, 0.f);
         }
         __syncthreads();                     /* previous coil's epilogue reads are done */
-        float2 *res = p2_fft<N, +1>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j, l) - l * PITCH;
+        float2 *res = p2_fft<N, +1, false>(v, bufA + l * PITCH, bufB + l * PITCH, stw, j, l) - l * PITCH;
 #pragma unroll
         for (int o = 0; o < OUTS; ++o) {
             const int idx = threadIdx.x + o * (L * T);
@@ -560,13 +578,13 @@ p2_adj_pass_b(const float2 *__restrict__ tmp, void *__restrict__ outv, const flo
 }
 
 template <int N, int L>
-__global__ void __launch_bounds__(L *(N / 8))
+__global__ void __launch_bounds__(L *(N / 8), (N >= 2048 && L * (N / 8) <= 1024 ? 2 : 1))
 p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const float *__restrict__ deapod,
               const float2 *__restrict__ tw, int nx, int nch, int nc_total, int ch0, int half_in, int chan_fastest)
 {
     extern __shared__ float2 smem[];
     constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
-    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
+    float2 *bufA = smem, *bufB = smem + (P2<N, L>::NBUF - 1) * L * PITCH, *stw = smem + P2<N, L>::NBUF * L * PITCH;
     const int l = threadIdx.x / T, j = threadIdx.x % T;
     /* many channels: the channel index runs fastest over the blocks (gridDim.x = planes), so that the blocks which
      * pick their channel's 4 or 8 bytes out of the same 32-byte sectors of the channel-interleaved image run
@@ -603,12 +621,12 @@ p2_fwd_pass_a(const void *__restrict__ imgv, float2 *__restrict__ tmp, const flo
 }
 
 template <int N, int L>
-__global__ void __launch_bounds__(L *(N / 8))
+__global__ void __launch_bounds__(L *(N / 8), (N >= 2048 && L * (N / 8) <= 1024 ? 2 : 1))
 p2_fwd_pass_b(const float2 *__restrict__ tmp, float2 *__restrict__ grid, const float2 *__restrict__ tw, int nx)
 {
     extern __shared__ float2 smem[];
     constexpr int T = P2<N, L>::T, PITCH = P2<N, L>::PITCH;
-    float2 *bufA = smem, *bufB = smem + L * PITCH, *stw = smem + 2 * L * PITCH;
+    float2 *bufA = smem, *bufB = smem + (P2<N, L>::NBUF - 1) * L * PITCH, *stw = smem + P2<N, L>::NBUF * L * PITCH;
     const int l = threadIdx.x / T, j = threadIdx.x % T;
     const int c0 = blockIdx.x * L;
     const int ch = blockIdx.y;
@@ -1155,13 +1173,14 @@ template <int N, int R1> struct P2WLaunch {
 template <int N> struct P2WSplit { static constexpr int R1 = N == 512 ? 32 : (N == 256 ? 16 : 0); };
 
 template <int N, int L> struct P2Launch {
-    static constexpr size_t SMEM = (size_t)(2 * L * P2<N, L>::PITCH + N + N / 8 + 1) * sizeof(float2);
+    static constexpr size_t SMEM = (size_t)(P2<N, L>::NBUF * L * P2<N, L>::PITCH + N + N / 8 + 1) * sizeof(float2);
+    static constexpr size_t SMEM_B = (size_t)(2 * L * P2<N, L>::PITCH + N + N / 8 + 1) * sizeof(float2);   /* adjoint pass B */
     static constexpr int THREADS = L * (N / 8);
     static int prepare()
     {
         TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_a<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_b<N, L, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_b<N, L, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_b<N, L, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_B));
+        TRON_CUDA(cudaFuncSetAttribute(p2_adj_pass_b<N, L, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_B));
         TRON_CUDA(cudaFuncSetAttribute(p2_fwd_pass_a<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         TRON_CUDA(cudaFuncSetAttribute(p2_fwd_pass_b<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         if constexpr (P2WSplit<N>::R1 != 0) { int rc = P2WLaunch<N, P2WSplit<N>::R1>::prepare(); if (rc) return rc; }
@@ -1188,10 +1207,10 @@ template <int N, int L> struct P2Launch {
         }
         dim3 gb((f.nkeep + L - 1) / L, a.nslices);
         if (2 * f.nkeep <= N)
-            p2_adj_pass_b<N, L, 4><<<gb, THREADS, SMEM, s>>>(a.tmp, a.out, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total,
+            p2_adj_pass_b<N, L, 4><<<gb, THREADS, SMEM_B, s>>>(a.tmp, a.out, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total,
                                                              a.ch0, a.mode, a.half_out);
         else
-            p2_adj_pass_b<N, L, 8><<<gb, THREADS, SMEM, s>>>(a.tmp, a.out, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total,
+            p2_adj_pass_b<N, L, 8><<<gb, THREADS, SMEM_B, s>>>(a.tmp, a.out, a.deapod, f.tw, f.nkeep, a.nch, a.nc_total,
                                                              a.ch0, a.mode, a.half_out);
         TRON_CUDA(cudaGetLastError());
         return 0;
