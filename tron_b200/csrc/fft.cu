@@ -1189,7 +1189,9 @@ template <int N, int L> struct P2Launch {
     static int adj(const FftPlan &f, const AdjFftLaunch &a, cudaStream_t s)
     {
         bool wide_a = false;
-        if constexpr (P2WSplit<N>::R1 != 0) wide_a = getenv("TRON_FFT_R8") == nullptr;
+        /* (a single plane gives the two-stage passes 64 / 32 blocks for 148 SMs: the radix-8 passes with their smaller
+         * blocks take 38 instead of 42 us for the 512^2 adjoint of BASELINE config 1) */
+        if constexpr (P2WSplit<N>::R1 != 0) wide_a = getenv("TRON_FFT_R8") == nullptr && (a.nslices * a.nch >= 4 || getenv("TRON_FFT_P2W") != nullptr);
         if constexpr (P2WSplit<N>::R1 != 0) {
             if (wide_a && a.sync && a.ring > 0 && 2 * f.nkeep == N && (a.mode == 0 || a.mode == 3))
                 return P2WLaunch<N, P2WSplit<N>::R1>::adj_fused(f, a, s);
