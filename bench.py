@@ -23,6 +23,7 @@ pointer).  One "step" = the whole 956-slice job.
   other_configs (N = 1): cfg1, cfg3 shard, cfg4 shard, cfg5 pair -- value, e2e,
            roofline and the reference's time for the same job (<= 6-coil chunks,
            sampled and scaled)
+  shards (N > 1): one cfg3 shard (32 slices, 32 coils) and one cfg4 shard (250 frames, 16 coils) per GPU
   strong / coil_sharded (N > 1): ONE cfg2 acquisition sharded by slice; the cfg5
            pair with 64/N coils per GPU and the library's single ncclReduce
   cpu_baseline: OpenMP C gridding operator (oracle/, "port") on the host cores,
@@ -191,11 +192,13 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
-def make_input(torch, n_elems, rank):
+def make_input(torch, n_elems, rank, pinned=True):
     """complex64 N(0,1) acquisition, generated on the device, returned as (device f32 tensor, pinned host copy)."""
     g = torch.Generator(device="cuda")
     g.manual_seed(20261017 + 2 + 1000 * rank)
     d = torch.randn(n_elems * 2, dtype=torch.float32, device="cuda", generator=g)
+    if not pinned:
+        return d, None
     h = torch.empty(n_elems * 2, dtype=torch.float32, pin_memory=True)
     h.copy_(d)
     torch.cuda.synchronize()
@@ -410,6 +413,27 @@ def measure_adjoint_config(torch, t, name, local, steps=3, warmup=2, with_refere
         if ref_ms:
             out["speedup_vs_reference_e2e"] = ref_ms / e2e_ms
     return out
+
+
+def shard_leg(torch, t, name, rank, world, local, steps=5, warmup=3):
+    """One per-GPU shard of BASELINE cfg3 / cfg4 on every rank at once (device resident; the N = 1 line carries the
+    end-to-end leg and the reference's time for the same shard)."""
+    dims, flags, desc = WORKLOADS[name]
+    plan = t.Plan(t.make_config(dims, device=local, **flags))
+    g = plan.geom.as_dict()
+    nsamp = g["nc"] * g["nro"] * g["npe1work"] * g["nz"]
+    d_in, _ = make_input(torch, g["shard_in_elems"], 7 + rank, pinned=False)
+    d_out = torch.zeros(g["shard_out_elems"] * 2, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = time_device(torch, lambda: plan.recon_device(d_out.data_ptr(), d_in.data_ptr(), stream), steps, warmup, world)
+    B = min(256, g["nz"])
+    kern = "grid_scatter_kernel" if g["nc"] in (2, 4, 6, 16) else ("grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel")
+    roof, grid_ms = grid_roofline(torch, plan, g, d_in, False, B, kern, name)
+    plan.close()
+    del d_in, d_out
+    return {"workload": desc + " -- one shard per GPU", "scaling": "weak", "value": nsamp * world / (ms * 1e-3),
+            "unit": "samples/s", "ms_per_step": ms, "images_per_s": g["nz"] * world / (ms * 1e-3),
+            "roofline_rank0": {k: roof[k] for k in ("kernel", "achieved", "peak", "unit", "frac", "ms_per_launch")}}
 
 
 def measure_cfg1(torch, t, local, steps=20, warmup=5):
@@ -747,6 +771,16 @@ def run_ours(args):
             except Exception as e:
                 extras["strong"] = {"error": "%s: %s" % (type(e).__name__, e)}
             torch.cuda.empty_cache()
+            # cfg3 / cfg4 are DEFINED as per-GPU shards of a larger job (256 slices / 2000 frames over 8 GPUs): every rank
+            # runs its shard, no collective; value = all ranks' samples over the slowest rank's time
+            shards = {}
+            for name in ("cfg3", "cfg4"):
+                try:
+                    shards[name] = shard_leg(torch, t, name, rank, world, local)
+                except Exception as e:
+                    shards[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.empty_cache()
+            extras["shards"] = shards
             try:
                 comm = make_comm(torch, t, rank, world, local)
                 pair = Cfg5Pair(torch, t, rank, world, local, comm)
