@@ -150,6 +150,7 @@ __device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], WideLis
     constexpr int STEP = DEPTH * EPI;                /* <= 8 */
     if (cnt == 0) return;
     const int padded = ((cnt + STEP - 1) / STEP) * STEP;     /* <= WCAP: WCAP is a multiple of STEP */
+    __syncwarp();                                    /* the entries other lanes appended (the pad copies the last offset) */
     if (cnt + lane < padded + STEP) {                /* (offsets one step further: the loads run one step ahead) */
         if (cnt + lane < padded) {
             L.wa[cnt + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
