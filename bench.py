@@ -239,14 +239,18 @@ def parity_vs_reference(torch, d_out, d_in, dims, flags, g, slices):
     (oracle/_ref) run on the same windows of the same input.  Slice z of a sliding-window job is the
     reference's single-slice job on spokes [z*slide, z*slide + npe1work) with skip_angles = z*slide
     (absolute golden-angle index, tron.cu:630,738)."""
+    nc, nro, win, slide = g["nc"], g["nro"], g["npe1work"], g["prof_slide"]
+    against = "oracle/_ref (unmodified tron.cu + cuFFT on this GPU), same input windows"
     try:
         from oracle.oracle import RefLib
         ref = RefLib()
+        if nc > ref.maxchan:           # tron.h:51 MAXCHAN 6: the same sources compiled with -DMAXCHAN=64 (oracle/build.py)
+            ref = RefLib(widened=True)
+            against = "oracle/_ref built with -DMAXCHAN=64 (tron.h:51; otherwise unmodified tron.cu + cuFFT), same input windows"
     except Exception as e:
         return {"unavailable": "oracle/_ref not built: %s" % e}
-    nc, nro, win, slide = g["nc"], g["nro"], g["npe1work"], g["prof_slide"]
     if nc > ref.maxchan:
-        return {"unavailable": "nc = %d > MAXCHAN of the stock reference" % nc}
+        return {"unavailable": "nc = %d > MAXCHAN of the reference builds" % nc}
     npix = g["nx"] * g["ny"]
     worst, per = 0.0, {}
     for z in slices:
@@ -259,8 +263,7 @@ def parity_vs_reference(torch, d_out, d_in, dims, flags, g, slices):
         got = d_out[2 * npix * z: 2 * npix * (z + 1)].cpu()
         per[str(z)] = rel_l2_t(got, want)
         worst = max(worst, per[str(z)])
-    return {"rel_l2": worst, "tolerance": 1e-5, "ok": bool(worst <= 1e-5), "slices": per,
-            "against": "oracle/_ref (unmodified tron.cu + cuFFT on this GPU), same input windows"}
+    return {"rel_l2": worst, "tolerance": 1e-5, "ok": bool(worst <= 1e-5), "slices": per, "against": against}
 
 
 def copy_floor_ms(torch, h_in, d_in, h_out, d_out, reps, world):
@@ -400,6 +403,12 @@ def measure_adjoint_config(torch, t, name, local, steps=3, warmup=2, with_refere
                    "h2d_bytes_per_step": in_elems * 8, "d2h_bytes_per_step": out_elems * 8,
                    "rel_l2_vs_device": rel_l2_t(h_out, d_out.cpu())},
            "roofline": roof}
+    try:                                        # checker, untimed: first and last slice of the device-resident output
+        plan.recon_device(d_out.data_ptr(), d_in.data_ptr(), stream)
+        torch.cuda.synchronize()
+        out["parity"] = parity_vs_reference(torch, d_out, d_in, dims, flags, g, sorted({0, g["nz"] - 1}))
+    except Exception as e:
+        out["parity"] = {"error": "%s: %s" % (type(e).__name__, e)}
     plan.close()
     del d_in, d_out, h_in, h_out
     torch.cuda.empty_cache()
