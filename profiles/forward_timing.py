@@ -8,6 +8,10 @@ CASES = {
     'cfg1_adj':  ([1, 1, 512, 512, 1], dict(adjoint=True)),
     'cfg5_fwd8': ([8, 1, 1024, 1024, 1], dict(adjoint=False, kernwidth=6.0, half_in=True, half_out=True)),
     'cfg5_adj8': ([8, 1, 2048, 2048, 1], dict(adjoint=True, kernwidth=6.0, half_in=True)),
+    'cfg5_fwd16': ([16, 1, 1024, 1024, 1], dict(adjoint=False, kernwidth=6.0, half_in=True, half_out=True)),
+    'cfg5_adj16': ([16, 1, 2048, 2048, 1], dict(adjoint=True, kernwidth=6.0, half_in=True)),
+    'cfg5_fwd32': ([32, 1, 1024, 1024, 1], dict(adjoint=False, kernwidth=6.0, half_in=True, half_out=True)),
+    'cfg5_adj32': ([32, 1, 2048, 2048, 1], dict(adjoint=True, kernwidth=6.0, half_in=True)),
     'cfg5_fwd64': ([64, 1, 1024, 1024, 1], dict(adjoint=False, kernwidth=6.0, half_in=True, half_out=True)),
     'cfg5_adj64': ([64, 1, 2048, 2048, 1], dict(adjoint=True, kernwidth=6.0, half_in=True)),
 }
