@@ -684,6 +684,28 @@ def test_wide_channel_degridding_vs_reference(lib, reflib, nc, flags):
         assert np.array_equal(other != 0, want != 0)
 
 
+@pytest.mark.parametrize("nc,dims_tail,flags", [
+    (32, [72, 40, 1], dict(adjoint=True, golden=True)),                  # 72 x 72 grid: the last 16 x 16 tiles are half outside
+    (64, [40, 36, 1], dict(adjoint=True, kernwidth=3.0)),                # 40 x 40 grid, two channels per lane
+    (8, [40, 36, 1], dict(adjoint=True, kernwidth=6.0)),
+    (32, [30, 30, 1], dict(adjoint=False, undersamp=0.55)),              # 33 spokes: the last pair is half empty
+    (64, [20, 20, 1], dict(adjoint=False, kernwidth=6.0, undersamp=0.825)),
+])
+def test_wide_kernels_on_ragged_shapes(lib, reflib, reflib_wide, nc, dims_tail, flags):
+    """Grids that are not a multiple of the 16 x 16 tile (the shared-memory output transpose must not store past the
+    edge) and spoke counts that are not a multiple of the spokes per warp / per block."""
+    import tron_b200 as t
+    torch_cuda()
+    dims = [nc, 1] + dims_tail
+    h_in = synth_complex((int(np.prod(dims)),), stream=900 + nc + dims_tail[0])
+    want = run_ref(reflib_wide if flags["adjoint"] else reflib, dims, flags, h_in)
+    with t.Plan(flags_to_cfg(dims, flags)) as p:
+        got = p.recon_host(h_in)
+    assert rel_l2(got, want) <= TOL_F32, rel_l2(got, want)
+    if not flags["adjoint"]:
+        assert np.array_equal(got != 0, want != 0)
+
+
 def test_shepp_logan_round_trip(lib, reflib):
     """BASELINE config 1: forward (RUNME1 flags = defaults) then adjoint on a 256^2 Shepp-Logan phantom,
     both steps against the reference; the golden-angle pair (-G / -a -G) must give back the phantom."""
