@@ -393,7 +393,7 @@ def measure_adjoint_config(torch, t, name, local, steps=3, warmup=2, with_refere
     ms = time_device(torch, lambda: plan.recon_device(d_out.data_ptr(), d_in.data_ptr(), stream), steps, warmup)
     launches = plan.last_launches()
     e2e_ms = time_wall(torch, lambda: plan.recon_host_ptr(h_out.data_ptr(), h_in.data_ptr()), steps, 1)
-    B = min(256, g["nz"])
+    B = min(plan.batch_slices(), g["nz"])
     kern = "grid_scatter_kernel" if g["nc"] in (2, 4, 6, 16) else ("grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel")
     roof, grid_ms = grid_roofline(torch, plan, g, d_in, False, B, kern, name)
     roof["share_of_step"] = grid_ms * (g["nz"] / B) / ms
@@ -435,7 +435,7 @@ def shard_leg(torch, t, name, rank, world, local, steps=5, warmup=3):
     d_out = torch.zeros(g["shard_out_elems"] * 2, dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     ms = time_device(torch, lambda: plan.recon_device(d_out.data_ptr(), d_in.data_ptr(), stream), steps, warmup, world)
-    B = min(256, g["nz"])
+    B = min(plan.batch_slices(), g["nz"])
     kern = "grid_scatter_kernel" if g["nc"] in (2, 4, 6, 16) else ("grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel")
     roof, grid_ms = grid_roofline(torch, plan, g, d_in, False, B, kern, name)
     plan.close()
@@ -700,7 +700,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     # ---- roofline of the dominant kernel (gridding), timed alone on this stream
-    B = min(256, g["nz"])                                          # the launch length the device pipeline uses
+    B = min(plan.batch_slices(), g["nz"])                          # the launch length the device pipeline uses
     kern = "grid_scatter_kernel" if g["nc"] in (2, 4, 6, 16) else ("grid_wide_kernel" if g["nc"] >= 32 else "grid_gather_kernel")
     roofline, grid_ms = grid_roofline(torch, plan, g, d_in, False, B, kern, args.workload)
     roofline["share_of_step"] = grid_ms * (g["nz"] / B) / ms_per_step

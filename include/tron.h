@@ -147,6 +147,8 @@ int  tron_coilcombine_walsh_device(void *d_img, const void *d_coilimg, int nimg,
 int  tron_plan_last_stage_ms(tron_plan *plan, float ms[3]);
 /* number of kernel launches issued by the last tron_recon_* call */
 int  tron_plan_last_launches(const tron_plan *plan);
+/* slices per launch of the device-resident pipeline (tron_recon_device); the host pipeline's batches are shorter */
+int  tron_plan_batch_slices(const tron_plan *plan);
 /* diagnostic (plan created with TRON_GRID_DEBUG set): per-warp cycle counts of the last gridding launch */
 int  tron_plan_grid_debug(tron_plan *plan, long long *h_cycles, int nwarps);
 

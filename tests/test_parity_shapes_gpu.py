@@ -31,9 +31,10 @@ def _device_recon(t, torch, p, h_in):
     return d_out.cpu().numpy().view(np.complex64)
 
 
-@pytest.mark.parametrize("k", [32, 64, 256])
+@pytest.mark.parametrize("k", [32, 64, 256, 480])
 def test_cfg2_launch_lengths_device_and_host(lib, reflib, k):
-    """k slices of the cfg2 geometry in ONE device launch (the bench uses 256) and through the host pipeline's
+    """k slices of the cfg2 geometry in ONE device launch (the bench's are 512 + 444; from 448 slices on the plan
+    uses chains of 64) and through the host pipeline's
     ramped batches; both against the reference, slice by slice, and against each other."""
     import tron_b200 as t
     torch = torch_cuda()

@@ -67,7 +67,7 @@ EXPORTED_SYMBOLS = [
     # tron.h: plan API
     "tron_config_defaults", "tron_geometry_compute", "tron_plan_create", "tron_plan_destroy",
     "tron_plan_geometry", "tron_recon_host", "tron_recon_device", "tron_grid_device",
-    "tron_grid_to_interleaved", "tron_degrid_device", "tron_plan_last_stage_ms", "tron_plan_last_launches",
+    "tron_grid_to_interleaved", "tron_degrid_device", "tron_plan_last_stage_ms", "tron_plan_last_launches", "tron_plan_batch_slices",
     "tron_plan_grid_debug", "tron_coilcombine_sos_device", "tron_coilcombine_walsh_device",
     "tron_last_error", "tron_version",
     # tron.h: coil-sharded root sum of squares (NCCL)
@@ -116,6 +116,8 @@ def load_library(path=None):
     L.tron_cgnr_radial2d.restype = None
     L.tron_plan_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tron_plan_last_launches.argtypes = [C.c_void_p]
+    L.tron_plan_batch_slices.argtypes = [C.c_void_p]
+    L.tron_plan_batch_slices.restype = C.c_int
     L.tron_set_config.argtypes = [C.POINTER(Config)]
     L.tron_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
     L.tron_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
@@ -288,6 +290,10 @@ class Plan:
 
     def last_launches(self):
         return int(self.lib.tron_plan_last_launches(self.handle))
+
+    def batch_slices(self):
+        """Slices per launch of the device-resident pipeline."""
+        return int(self.lib.tron_plan_batch_slices(self.handle))
 
     def last_stage_ms(self):
         """(gridding/degridding, FFT passes, other) device ms of the last recon_device call;

@@ -205,7 +205,9 @@ int scatter_plan_build(ScatterPlan &sp, const int2 *cells, int nbins, int n, int
         sp.ne_delta = 2 * slide;
         rc = build_scatter_table(&sp.tab_delta, &sp.lut_delta, nslices, sp.ne_delta, 1, 1, skip, golden, nbins, win, slide, nslices, s);
         if (rc) return rc;
-        sp.chain = env_chain > 1 ? env_chain : 32;
+        /* long jobs (launches of ~500 slices): chains of 64 -- 44.6 instead of 47.1 spoke visits per slice, and still
+         * enough (tile, chain) tasks; shorter jobs keep 32 (256-slice launches: 1.30 vs 1.08 ms with 64) */
+        sp.chain = env_chain > 1 ? env_chain : (nslices >= 448 ? 64 : 32);
         sp.chain_near = env_chain_near > 0 ? env_chain_near : 16;
         if (sp.chain_near > sp.chain) sp.chain_near = sp.chain;
         while (sp.chain % sp.chain_near) --sp.chain_near;      /* near chains nest in the far ones */

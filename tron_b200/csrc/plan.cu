@@ -179,11 +179,14 @@ static int pick_batch(const tron_plan *p)
      * longer launches still shave the drain of each kernel (measured on cfg2, device resident: 10.31 ms per
      * step at 64 slices per launch, 10.02 at 128); the work buffers are bounded to ~6 GB of the 180 GB.
      * The host pipeline caps its launches at HOST_BATCH_MAX (copy/compute overlap wants them shorter). */
-    size_t budget = (size_t)6144 << 20, freeb = 0, totalb = 0;
+    /* Round 2: with the scatter kernel's (tile, chain) tasks a 512-slice launch has a shorter tail than two of 256 and
+     * allows chains of 64 (7.8 instead of 8.0-8.1 ms per cfg2 step; TRON_BATCH x TRON_SCATTER_CHAIN sweep in
+     * profiles/r02_batch_chain_sweep.txt): up to 512 slices within 12 GB. */
+    size_t budget = (size_t)12288 << 20, freeb = 0, totalb = 0;
     if (cudaMemGetInfo(&freeb, &totalb) == cudaSuccess && freeb / 3 < budget) budget = freeb / 3;   /* shared GPUs */
     size_t b = budget / (per ? per : 1);
     if (b < 1) b = 1;
-    if (b > 256) b = 256;
+    if (b > 512) b = 512;
     if ((int)b > p->nslices) b = p->nslices;
     return (int)b;
 }
@@ -729,6 +732,7 @@ extern "C" int tron_plan_last_stage_ms(tron_plan *p, float ms[3])
 }
 
 extern "C" int tron_plan_last_launches(const tron_plan *p) { return p ? p->last_launches : 0; }
+extern "C" int tron_plan_batch_slices(const tron_plan *p) { return p ? p->batch : 0; }
 
 /* diagnostic: copy out the per-warp cycle counts of the last gridding launch (TRON_GRID_DEBUG) */
 extern "C" int tron_plan_grid_debug(tron_plan *p, long long *h_cycles, int nwarps)
