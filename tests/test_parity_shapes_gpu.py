@@ -136,6 +136,49 @@ def _from_half_pairs(h):
     return (f[:, 0] + 1j * f[:, 1]).astype(np.complex64)
 
 
+def test_cfg5_line_length_2048_forward_and_adjoint(lib, reflib, reflib_wide):
+    """cfg5's own grid, 2048 x 2048 (1024 matrix, 2x): the 2048-point FFT passes (4 lines per block, single exchange
+    buffer, channel-fastest block order from 8 channels on) against the reference, forward and adjoint, 8 coils,
+    default kernel width (the reference's adjoint kernel visits every spoke for every cell: -k 6 at this size
+    would take minutes)."""
+    import tron_b200 as t
+    torch_cuda()
+    nc, nx = 8, 1024
+    fdims = [nc, 1, nx, nx, 1]
+    fflags = dict(adjoint=False, undersamp=0.0625)                      # 128 spokes of 2048 samples
+    img = synth_complex((int(np.prod(fdims)),), stream=660)
+    want_s = run_ref(reflib, fdims, fflags, img)
+    with t.Plan(flags_to_cfg(fdims, fflags)) as p:
+        assert p.geom.nxos == 2048 and p.geom.nro == 2048 and p.geom.npe1work == 128
+        got_s = p.recon_host(img)
+    assert rel_l2(got_s, want_s) <= TOL_F32, rel_l2(got_s, want_s)
+    adims = [nc, 1, 2048, 128, 1]
+    aflags = dict(adjoint=True, undersamp=0.0625)
+    s = (want_s * (1.0 / np.abs(want_s).max())).astype(np.complex64)
+    want_i = run_ref(reflib_wide, adims, aflags, s)
+    with t.Plan(flags_to_cfg(adims, aflags)) as p:
+        assert p.geom.nxos == 2048 and p.geom.nx == 1024 and p.geom.npe1work == 128
+        got_i = p.recon_host(s)
+    assert rel_l2(got_i, want_i) <= TOL_F32, rel_l2(got_i, want_i)
+    with t.Plan(flags_to_cfg(adims, aflags, per_coil_out=True)) as p:   # per-coil images: pass B without the coil sum
+        got_c = p.recon_host(s)
+    assert rel_l2(np.sqrt((np.abs(got_c.reshape(-1, nc)) ** 2).sum(axis=1)), want_i.real) <= TOL_F32
+
+
+def test_line_length_4096_forward(lib, reflib):
+    """The longest power-of-two line (one line per block, 512 threads, single exchange buffer): 2048 matrix, one coil."""
+    import tron_b200 as t
+    torch_cuda()
+    fdims = [1, 1, 2048, 2048, 1]
+    fflags = dict(adjoint=False, undersamp=0.0078125)                   # 32 spokes of 4096 samples
+    img = synth_complex((int(np.prod(fdims)),), stream=661)
+    want_s = run_ref(reflib, fdims, fflags, img)
+    with t.Plan(flags_to_cfg(fdims, fflags)) as p:
+        assert p.geom.nxos == 4096 and p.geom.npe1work == 32
+        got_s = p.recon_host(img)
+    assert rel_l2(got_s, want_s) <= TOL_F32, rel_l2(got_s, want_s)
+
+
 def test_cfg5_shape_fp16_forward_and_adjoint(lib, reflib, reflib_wide):
     """64 coils, kernel width 6, fp16 storage, 512^2 oversampled grid (a quarter of cfg5's matrix): forward and
     adjoint, each against the reference run on the same fp16-rounded input in fp32."""
