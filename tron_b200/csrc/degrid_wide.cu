@@ -288,6 +288,143 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
     }
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * 8 channels (cfg5's coil shards on 8 GPUs).  In the kernel above the four quarter-warps take four ROWS of the window
+ * at a time: every request is four 64-byte pieces of four different rows and the weights of four rows -- ncu: the L1
+ * data pipe 91 % busy, 2.5 wavefronts per cell for four FFMA2.  Here the quarter-warps take four ADJACENT COLUMNS of
+ * one row: in the channel-interleaved grid that is one contiguous 256-byte piece (two wavefronts for four cells), and
+ * the four weights are neighbours in shared memory.  Loads run one step (16 columns) ahead, across rows.
+ * ------------------------------------------------------------------------------------------------------------- */
+struct __align__(16) Dw8Weights {
+    float4 wx[DW_MAXU];      /* row factor of samples 0..3 */
+    float4 wy[32];           /* column factor, zero past the window */
+    float4 wp[32];           /* wx[row] * wy[column] of the row in flight */
+    int coffT[32];           /* wrapped column indices, [step of 16][quarter-warp][quad]: one 16-byte load per lane */
+};
+
+template <bool HALF>
+__global__ void __launch_bounds__(256)
+degrid_wide8_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interleaved grid, 8 channels */)
+{
+    __shared__ Dw8Weights sw8[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Dw8Weights &S = sw8[warp];
+    const int n = d.n;
+    const int groups_per_spoke = (d.nro + DW_S - 1) / DW_S;
+    const float W = d.kb.W;
+    const float c0 = (float)((n + 1) / 2);
+    const float inv_nro = rcp_approx((float)d.nro);
+    const int clane = lane & 7, rsub = lane >> 3;        /* channel, quarter-warp = column inside a quad of columns */
+    const long long nwork = (long long)((d.npe + 7) / 8) * groups_per_spoke;
+    for (long long wb = blockIdx.x; wb < nwork; wb += gridDim.x) {
+        const int pe = (int)(wb / groups_per_spoke) * 8 + warp;
+        const int ro0 = (int)(wb % groups_per_spoke) * DW_S;
+        if (pe >= d.npe) continue;
+        const float2 cs = __ldg(d.cs + pe);
+        /* coordinates of the four samples, exactly as tron.cu:554-561 compiles */
+        float X[DW_S], Y[DW_S];
+        int xlo = 1 << 30, xhi = -(1 << 30), ylo = 1 << 30, yhi = -(1 << 30);
+#pragma unroll
+        for (int k = 0; k < DW_S; ++k) {
+            const float R = fma_ftz((float)(ro0 + k), inv_nro, -0.5f);
+            const float nR = mul_ftz(R, (float)n);
+            X[k] = fma_ftz(cs.y, nR, c0);            /* rows:    sin */
+            Y[k] = fma_ftz(cs.x, nR, c0);            /* columns: cos */
+            if (ro0 + k < d.nro) {
+                xlo = min(xlo, (int)ceilf(X[k] - W)); xhi = max(xhi, (int)floorf(X[k] + W));
+                ylo = min(ylo, (int)ceilf(Y[k] - W)); yhi = max(yhi, (int)floorf(Y[k] + W));
+            }
+        }
+        const int nux = min(xhi - xlo + 1, DW_MAXU), nuy = min(yhi - ylo + 1, DW_MAXU);
+        const int nuyP = (nuy + 15) & ~15;                                      /* 16 or 32 columns */
+
+        /* phase A: lanes = rows, then columns */
+        __syncwarp();
+        for (int i = lane; i < nux + nuyP; i += 32) {
+            const bool isrow = i < nux;
+            const int c = i - nux;                                              /* column (when not a row) */
+            const int u = isrow ? xlo + i : ylo + min(c, nuy - 1);
+            float dd[DW_S], w4[DW_S];
+#pragma unroll
+            for (int k = 0; k < DW_S; ++k) dd[k] = (float)u - (isrow ? X[k] : Y[k]);
+            const float2 k01 = kb_weight_pair(dd[0], dd[1], d.kb), k23 = kb_weight_pair(dd[2], dd[3], d.kb);
+            const float kk[DW_S] = { k01.x, k01.y, k23.x, k23.y };
+#pragma unroll
+            for (int k = 0; k < DW_S; ++k) {
+                const bool live = (ro0 + k < d.nro) && fabsf(dd[k]) < W && (isrow || c < nuy);   /* tron.cu:343 via gridkernel */
+                w4[k] = live ? kk[k] : 0.f;
+            }
+            if (isrow) S.wx[i] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+            else {
+                S.wy[c] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+                /* column c = 16 step + 4 quad + quarter-warp: stored as [step][quarter-warp][quad] */
+                S.coffT[(c & ~15) + (c & 3) * 4 + ((c >> 2) & 3)] = wrap_cell_w(u, n);          /* periodic, tron.cu:570 */
+            }
+        }
+        __syncwarp();
+
+        /* phase B: lanes = (quarter-warp = column of a quad, channel) */
+        float2 acc[DW_S];
+#pragma unroll
+        for (int k = 0; k < DW_S; ++k) acc[k] = make_float2(0.f, 0.f);
+        const int sh = nuyP >> 5;                                               /* steps per row: 1 << sh */
+        const int nq = nux << sh;
+        auto load = [&](float2 (&v)[4], int q) {
+            const int i0 = q >> sh, st = q & ((1 << sh) - 1);
+            const int row = wrap_cell_w(xlo + i0, n);                           /* periodic, tron.cu:569 */
+            const char *base = (const char *)(gi + ((size_t)row * n) * 8 + clane);
+            const int4 co = *reinterpret_cast<const int4 *>(&S.coffT[st * 16 + rsub * 4]);
+            v[0] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.x * 64u));
+            v[1] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.y * 64u));
+            v[2] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.z * 64u));
+            v[3] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.w * 64u));
+        };
+        auto fma = [&](const float2 (&v)[4], int q) {
+            const int i0 = q >> sh, st = q & ((1 << sh) - 1);
+            if (st == 0) {                                                      /* a new row: its tap weights */
+                __syncwarp();
+                if (lane < nuyP) {
+                    const float4 a = S.wx[i0], b = S.wy[lane];
+                    S.wp[lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4 b = S.wp[st * 16 + 4 * jj + rsub];
+                ffma2d(acc[0], b.x, v[jj]); ffma2d(acc[1], b.y, v[jj]);
+                ffma2d(acc[2], b.z, v[jj]); ffma2d(acc[3], b.w, v[jj]);
+            }
+        };
+        float2 va[4], vb[4];
+        load(va, 0);
+        for (int q = 0; q < nq; q += 2) {
+            if (q + 1 < nq) load(vb, q + 1);
+            fma(va, q);
+            if (q + 1 >= nq) break;
+            if (q + 2 < nq) load(va, q + 2);
+            fma(vb, q + 1);
+        }
+        /* add the quarter-warps' partial sums */
+#pragma unroll
+        for (int k = 0; k < DW_S; ++k)
+#pragma unroll
+            for (int o = 8; o < 32; o <<= 1) {
+                acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
+                acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+            }
+        if (rsub == 0) {
+#pragma unroll
+            for (int k = 0; k < DW_S; ++k) {
+                if (ro0 + k >= d.nro) continue;
+                const size_t o = ((size_t)pe * d.nro + ro0 + k) * d.nc_total + d.ch0 + clane;
+                if (HALF) ((__half2 *)d.samples)[o] = __float22half2_rn(acc[k]);
+                else ((float2 *)d.samples)[o] = acc[k];
+            }
+        }
+    }
+}
+
 /* planar [ch][cell] -> interleaved [cell][ch], 32 x 32 tiles through shared memory */
 __global__ void __launch_bounds__(256)
 planar_to_interleaved_kernel(float2 *__restrict__ dst, const float2 *__restrict__ src, int nch, size_t ncell)
@@ -341,7 +478,10 @@ int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
     const int P = pair ? 2 : 1;
     const long long nwork = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 8 * P - 1) / (8 * P));
     int bx = (int)(nwork < 148 * 32 ? nwork : 148 * 32);
-    if (d.nch == 8) {
+    if (d.nch == 8 && !pair && getenv("TRON_DEGRID_ROWS8") == nullptr) {
+        if (d.half_out) degrid_wide8_kernel<true><<<bx, 256, 0, s>>>(d, scratch);
+        else            degrid_wide8_kernel<false><<<bx, 256, 0, s>>>(d, scratch);
+    } else if (d.nch == 8) {
         if (pair) launch_dw<1, 8, 2>(d, scratch, dim3(bx), s); else launch_dw<1, 8, 1>(d, scratch, dim3(bx), s);
     } else if (d.nch == 16) {
         if (pair) launch_dw<1, 16, 2>(d, scratch, dim3(bx), s); else launch_dw<1, 16, 1>(d, scratch, dim3(bx), s);
