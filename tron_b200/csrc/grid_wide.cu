@@ -29,6 +29,9 @@ namespace tronb {
 
 #define PI_F 3.14159274101257324219f
 #define WCAP 96                       /* list entries per warp */
+#ifndef WIDE_PIPE_SUB
+#define WIDE_PIPE_SUB 1               /* sub-warp instantiations (8 / 16 channels) with fp16 samples: pipelined drain (16-coil cfg5 shard 4.05 -> 2.85 ms; 32 channels per warp: 3.81 -> 4.00, stays off) */
+#endif
 
 struct __align__(16) WideList {
     float4 wa[WCAP];                  /* weights of cells (0..3, row 0) */
@@ -146,7 +149,7 @@ __device__ __forceinline__ void wide_drain(float2 (&acc)[NCHUNK][GS][8], WideLis
     constexpr int EPI = 32 / LPC;                    /* entries per step */
     /* one channel chunk (64-register instantiations, cfg3): the second buffer would spill -- 8 steps at a time, loads
      * then FMAs (measured: 2.91 vs 3.12 ms per 32 cfg3 slices) */
-    constexpr int DEPTH = !PIPE ? 8 / EPI : ((HALF || NCHUNK == 1) ? 4 : 2);
+    constexpr int DEPTH = !PIPE ? 8 / EPI : ((HALF || NCHUNK == 1) ? (EPI == 4 ? 2 : 4) : 2);
     constexpr int STEP = DEPTH * EPI;                /* <= 8 */
     if (cnt == 0) return;
     const int padded = ((cnt + STEP - 1) / STEP) * STEP;     /* <= WCAP: WCAP is a multiple of STEP */
@@ -367,12 +370,12 @@ grid_wide_kernel(const GridLaunch g)
                     }
                     cnt += __popc(hit);
                     if (cnt + 32 > WCAP) {                       /* phase B: lanes = channels */
-                        wide_drain<LPC, NCHUNK, GS, HALF, (NCHUNK == 2 || MINB == 3)>(acc, L, cnt, lbase, lane);
+                        wide_drain<LPC, NCHUNK, GS, HALF, (NCHUNK == 2 || MINB == 3 || (HALF && LPC < 32 && WIDE_PIPE_SUB))>(acc, L, cnt, lbase, lane);
                         cnt = 0;
                     }
                 }
             }
-            wide_drain<LPC, NCHUNK, GS, HALF, (NCHUNK == 2 || MINB == 3)>(acc, L, cnt, lbase, lane);
+            wide_drain<LPC, NCHUNK, GS, HALF, (NCHUNK == 2 || MINB == 3 || (HALF && LPC < 32 && WIDE_PIPE_SUB))>(acc, L, cnt, lbase, lane);
         }
 
         /* fold the two half-warps (nc = 16 mode), then every lane writes its channel plane */
