@@ -295,119 +295,152 @@ degrid_wide_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interl
  * one row: in the channel-interleaved grid that is one contiguous 256-byte piece (two wavefronts for four cells), and
  * the four weights are neighbours in shared memory.  Loads run one step (16 columns) ahead, across rows.
  * ------------------------------------------------------------------------------------------------------------- */
-struct __align__(16) Dw8Weights {
-    float4 wx[DW_MAXU];      /* row factor of samples 0..3 */
-    float4 wy[32];           /* column factor, zero past the window */
-    float4 wp[32];           /* wx[row] * wy[column] of the row in flight */
+template <int P> struct __align__(16) Dw8Weights {
+    float4 wx[P][DW_MAXU];   /* row factor of samples 0..3 of spoke p */
+    float4 wy[P][32];        /* column factor, zero past the window */
+    float4 wp[P][32];        /* wx[row] * wy[column] of the row in flight */
     int coffT[32];           /* wrapped column indices, [step of 16][quarter-warp][quad]: one 16-byte load per lane */
 };
 
-template <bool HALF>
+/* P = spokes per warp: with linear angle order the neighbours pe, pe + 1 share a window (see degrid_wide_kernel), a
+ * loaded cell and the row's bookkeeping then serve 8 samples -- this kernel is bound by issued instructions, not by
+ * L1.  A pair whose union window does not fit is walked spoke by spoke. */
+template <bool HALF, int P>
 __global__ void __launch_bounds__(256)
 degrid_wide8_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interleaved grid, 8 channels */)
 {
-    __shared__ Dw8Weights sw8[8];
+    constexpr int NS = P * DW_S;
+    __shared__ Dw8Weights<P> sw8[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Dw8Weights &S = sw8[warp];
+    Dw8Weights<P> &S = sw8[warp];
     const int n = d.n;
     const int groups_per_spoke = (d.nro + DW_S - 1) / DW_S;
     const float W = d.kb.W;
     const float c0 = (float)((n + 1) / 2);
     const float inv_nro = rcp_approx((float)d.nro);
     const int clane = lane & 7, rsub = lane >> 3;        /* channel, quarter-warp = column inside a quad of columns */
-    const long long nwork = (long long)((d.npe + 7) / 8) * groups_per_spoke;
+    const long long nwork = (long long)((d.npe + 8 * P - 1) / (8 * P)) * groups_per_spoke;
     for (long long wb = blockIdx.x; wb < nwork; wb += gridDim.x) {
-        const int pe = (int)(wb / groups_per_spoke) * 8 + warp;
+        const int pe0 = ((int)(wb / groups_per_spoke) * 8 + warp) * P;
         const int ro0 = (int)(wb % groups_per_spoke) * DW_S;
-        if (pe >= d.npe) continue;
-        const float2 cs = __ldg(d.cs + pe);
-        /* coordinates of the four samples, exactly as tron.cu:554-561 compiles */
-        float X[DW_S], Y[DW_S];
-        int xlo = 1 << 30, xhi = -(1 << 30), ylo = 1 << 30, yhi = -(1 << 30);
+        if (pe0 >= d.npe) continue;
+        /* coordinates of the samples, exactly as tron.cu:554-561 compiles */
+        float X[NS], Y[NS];
+        int bx0[P], bx1[P], by0[P], by1[P];
 #pragma unroll
-        for (int k = 0; k < DW_S; ++k) {
-            const float R = fma_ftz((float)(ro0 + k), inv_nro, -0.5f);
-            const float nR = mul_ftz(R, (float)n);
-            X[k] = fma_ftz(cs.y, nR, c0);            /* rows:    sin */
-            Y[k] = fma_ftz(cs.x, nR, c0);            /* columns: cos */
-            if (ro0 + k < d.nro) {
-                xlo = min(xlo, (int)ceilf(X[k] - W)); xhi = max(xhi, (int)floorf(X[k] + W));
-                ylo = min(ylo, (int)ceilf(Y[k] - W)); yhi = max(yhi, (int)floorf(Y[k] + W));
-            }
-        }
-        const int nux = min(xhi - xlo + 1, DW_MAXU), nuy = min(yhi - ylo + 1, DW_MAXU);
-        const int nuyP = (nuy + 15) & ~15;                                      /* 16 or 32 columns */
-
-        /* phase A: lanes = rows, then columns */
-        __syncwarp();
-        for (int i = lane; i < nux + nuyP; i += 32) {
-            const bool isrow = i < nux;
-            const int c = i - nux;                                              /* column (when not a row) */
-            const int u = isrow ? xlo + i : ylo + min(c, nuy - 1);
-            float dd[DW_S], w4[DW_S];
-#pragma unroll
-            for (int k = 0; k < DW_S; ++k) dd[k] = (float)u - (isrow ? X[k] : Y[k]);
-            const float2 k01 = kb_weight_pair(dd[0], dd[1], d.kb), k23 = kb_weight_pair(dd[2], dd[3], d.kb);
-            const float kk[DW_S] = { k01.x, k01.y, k23.x, k23.y };
+        for (int p = 0; p < P; ++p) {
+            const float2 cs = __ldg(d.cs + min(pe0 + p, d.npe - 1));
+            bx0[p] = by0[p] = 1 << 30; bx1[p] = by1[p] = -(1 << 30);
 #pragma unroll
             for (int k = 0; k < DW_S; ++k) {
-                const bool live = (ro0 + k < d.nro) && fabsf(dd[k]) < W && (isrow || c < nuy);   /* tron.cu:343 via gridkernel */
-                w4[k] = live ? kk[k] : 0.f;
-            }
-            if (isrow) S.wx[i] = make_float4(w4[0], w4[1], w4[2], w4[3]);
-            else {
-                S.wy[c] = make_float4(w4[0], w4[1], w4[2], w4[3]);
-                /* column c = 16 step + 4 quad + quarter-warp: stored as [step][quarter-warp][quad] */
-                S.coffT[(c & ~15) + (c & 3) * 4 + ((c >> 2) & 3)] = wrap_cell_w(u, n);          /* periodic, tron.cu:570 */
+                const int s = p * DW_S + k;
+                const float R = fma_ftz((float)(ro0 + k), inv_nro, -0.5f);
+                const float nR = mul_ftz(R, (float)n);
+                X[s] = fma_ftz(cs.y, nR, c0);            /* rows:    sin */
+                Y[s] = fma_ftz(cs.x, nR, c0);            /* columns: cos */
+                if (ro0 + k < d.nro && pe0 + p < d.npe) {
+                    bx0[p] = min(bx0[p], (int)ceilf(X[s] - W)); bx1[p] = max(bx1[p], (int)floorf(X[s] + W));
+                    by0[p] = min(by0[p], (int)ceilf(Y[s] - W)); by1[p] = max(by1[p], (int)floorf(Y[s] + W));
+                }
             }
         }
-        __syncwarp();
+        int npass = 1;
+        if (P > 1) {
+            int x0 = bx0[0], x1 = bx1[0], y0 = by0[0], y1 = by1[0];
+#pragma unroll
+            for (int p = 1; p < P; ++p) { x0 = min(x0, bx0[p]); x1 = max(x1, bx1[p]); y0 = min(y0, by0[p]); y1 = max(y1, by1[p]); }
+            if (x1 - x0 + 1 > DW_MAXU || y1 - y0 + 1 > DW_MAXU) npass = P;
+        }
+        float2 acc[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) acc[k] = make_float2(0.f, 0.f);
 
-        /* phase B: lanes = (quarter-warp = column of a quad, channel) */
-        float2 acc[DW_S];
+        for (int pass = 0; pass < npass; ++pass) {
+            int xlo = 1 << 30, xhi = -(1 << 30), ylo = 1 << 30, yhi = -(1 << 30);
 #pragma unroll
-        for (int k = 0; k < DW_S; ++k) acc[k] = make_float2(0.f, 0.f);
-        const int sh = nuyP >> 5;                                               /* steps per row: 1 << sh */
-        const int nq = nux << sh;
-        auto load = [&](float2 (&v)[4], int q) {
-            const int i0 = q >> sh, st = q & ((1 << sh) - 1);
-            const int row = wrap_cell_w(xlo + i0, n);                           /* periodic, tron.cu:569 */
-            const char *base = (const char *)(gi + ((size_t)row * n) * 8 + clane);
-            const int4 co = *reinterpret_cast<const int4 *>(&S.coffT[st * 16 + rsub * 4]);
-            v[0] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.x * 64u));
-            v[1] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.y * 64u));
-            v[2] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.z * 64u));
-            v[3] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.w * 64u));
-        };
-        auto fma = [&](const float2 (&v)[4], int q) {
-            const int i0 = q >> sh, st = q & ((1 << sh) - 1);
-            if (st == 0) {                                                      /* a new row: its tap weights */
-                __syncwarp();
-                if (lane < nuyP) {
-                    const float4 a = S.wx[i0], b = S.wy[lane];
-                    S.wp[lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+            for (int p = 0; p < P; ++p)
+                if (npass == 1 || p == pass) {
+                    xlo = min(xlo, bx0[p]); xhi = max(xhi, bx1[p]); ylo = min(ylo, by0[p]); yhi = max(yhi, by1[p]);
                 }
-                __syncwarp();
-            }
+            if (xhi < xlo) continue;                                            /* (a spoke past the last one) */
+            const int nux = min(xhi - xlo + 1, DW_MAXU), nuy = min(yhi - ylo + 1, DW_MAXU);
+            const int nuyP = (nuy + 15) & ~15;                                  /* 16 or 32 columns */
+
+            /* phase A: lanes = rows, then columns */
+            __syncwarp();
+            for (int i = lane; i < nux + nuyP; i += 32) {
+                const bool isrow = i < nux;
+                const int c = i - nux;                                          /* column (when not a row) */
+                const int u = isrow ? xlo + i : ylo + min(c, nuy - 1);
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const float4 b = S.wp[st * 16 + 4 * jj + rsub];
-                ffma2d(acc[0], b.x, v[jj]); ffma2d(acc[1], b.y, v[jj]);
-                ffma2d(acc[2], b.z, v[jj]); ffma2d(acc[3], b.w, v[jj]);
+                for (int p = 0; p < P; ++p) {
+                    float dd[DW_S], w4[DW_S];
+#pragma unroll
+                    for (int k = 0; k < DW_S; ++k) dd[k] = (float)u - (isrow ? X[p * DW_S + k] : Y[p * DW_S + k]);
+                    const float2 k01 = kb_weight_pair(dd[0], dd[1], d.kb), k23 = kb_weight_pair(dd[2], dd[3], d.kb);
+                    const float kk[DW_S] = { k01.x, k01.y, k23.x, k23.y };
+#pragma unroll
+                    for (int k = 0; k < DW_S; ++k) {
+                        const bool live = (ro0 + k < d.nro) && (pe0 + p < d.npe) && (npass == 1 || p == pass)
+                            && fabsf(dd[k]) < W && (isrow || c < nuy);           /* tron.cu:343 via gridkernel */
+                        w4[k] = live ? kk[k] : 0.f;
+                    }
+                    if (isrow) S.wx[p][i] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+                    else S.wy[p][c] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                /* column c = 16 step + 4 quad + quarter-warp: stored as [step][quarter-warp][quad] */
+                if (!isrow) S.coffT[(c & ~15) + (c & 3) * 4 + ((c >> 2) & 3)] = wrap_cell_w(u, n);   /* periodic, tron.cu:570 */
             }
-        };
-        float2 va[4], vb[4];
-        load(va, 0);
-        for (int q = 0; q < nq; q += 2) {
-            if (q + 1 < nq) load(vb, q + 1);
-            fma(va, q);
-            if (q + 1 >= nq) break;
-            if (q + 2 < nq) load(va, q + 2);
-            fma(vb, q + 1);
+            __syncwarp();
+
+            /* phase B: lanes = (quarter-warp = column of a quad, channel) */
+            const int sh = nuyP >> 5;                                           /* steps per row: 1 << sh */
+            const int nq = nux << sh;
+            auto load = [&](float2 (&v)[4], int q) {
+                const int i0 = q >> sh, st = q & ((1 << sh) - 1);
+                const int row = wrap_cell_w(xlo + i0, n);                       /* periodic, tron.cu:569 */
+                const char *base = (const char *)(gi + ((size_t)row * n) * 8 + clane);
+                const int4 co = *reinterpret_cast<const int4 *>(&S.coffT[st * 16 + rsub * 4]);
+                v[0] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.x * 64u));
+                v[1] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.y * 64u));
+                v[2] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.z * 64u));
+                v[3] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.w * 64u));
+            };
+            auto fma = [&](const float2 (&v)[4], int q) {
+                const int i0 = q >> sh, st = q & ((1 << sh) - 1);
+                if (st == 0) {                                                  /* a new row: its tap weights */
+                    __syncwarp();
+                    if (lane < nuyP) {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            const float4 a = S.wx[p][i0], b = S.wy[p][lane];
+                            S.wp[p][lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+                        }
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const float4 b = S.wp[p][st * 16 + 4 * jj + rsub];
+                        ffma2d(acc[4 * p + 0], b.x, v[jj]); ffma2d(acc[4 * p + 1], b.y, v[jj]);
+                        ffma2d(acc[4 * p + 2], b.z, v[jj]); ffma2d(acc[4 * p + 3], b.w, v[jj]);
+                    }
+            };
+            float2 va[4], vb[4];
+            load(va, 0);
+            for (int q = 0; q < nq; q += 2) {
+                if (q + 1 < nq) load(vb, q + 1);
+                fma(va, q);
+                if (q + 1 >= nq) break;
+                if (q + 2 < nq) load(va, q + 2);
+                fma(vb, q + 1);
+            }
         }
         /* add the quarter-warps' partial sums */
 #pragma unroll
-        for (int k = 0; k < DW_S; ++k)
+        for (int k = 0; k < NS; ++k)
 #pragma unroll
             for (int o = 8; o < 32; o <<= 1) {
                 acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
@@ -415,9 +448,10 @@ degrid_wide8_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* inter
             }
         if (rsub == 0) {
 #pragma unroll
-            for (int k = 0; k < DW_S; ++k) {
-                if (ro0 + k >= d.nro) continue;
-                const size_t o = ((size_t)pe * d.nro + ro0 + k) * d.nc_total + d.ch0 + clane;
+            for (int k = 0; k < NS; ++k) {
+                const int pe = pe0 + k / DW_S, ro = ro0 + k % DW_S;
+                if (ro >= d.nro || pe >= d.npe) continue;
+                const size_t o = ((size_t)pe * d.nro + ro) * d.nc_total + d.ch0 + clane;
                 if (HALF) ((__half2 *)d.samples)[o] = __float22half2_rn(acc[k]);
                 else ((float2 *)d.samples)[o] = acc[k];
             }
@@ -478,9 +512,18 @@ int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
     const int P = pair ? 2 : 1;
     const long long nwork = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 8 * P - 1) / (8 * P));
     int bx = (int)(nwork < 148 * 32 ? nwork : 148 * 32);
-    if (d.nch == 8 && !pair && getenv("TRON_DEGRID_ROWS8") == nullptr) {
-        if (d.half_out) degrid_wide8_kernel<true><<<bx, 256, 0, s>>>(d, scratch);
-        else            degrid_wide8_kernel<false><<<bx, 256, 0, s>>>(d, scratch);
+    if (d.nch == 8 && getenv("TRON_DEGRID_ROWS8") == nullptr) {
+        /* (the column kernel pairs spokes whenever the angle order is linear: it is bound by instructions, not L1) */
+        const bool pair8 = pair_env >= 0 ? pair_env != 0 : d.pair_spokes != 0;
+        const long long nw8 = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + (pair8 ? 16 : 8) - 1) / (pair8 ? 16 : 8));
+        const int b8 = (int)(nw8 < 148 * 32 ? nw8 : 148 * 32);
+        if (pair8) {
+            if (d.half_out) degrid_wide8_kernel<true, 2><<<b8, 256, 0, s>>>(d, scratch);
+            else            degrid_wide8_kernel<false, 2><<<b8, 256, 0, s>>>(d, scratch);
+        } else {
+            if (d.half_out) degrid_wide8_kernel<true, 1><<<b8, 256, 0, s>>>(d, scratch);
+            else            degrid_wide8_kernel<false, 1><<<b8, 256, 0, s>>>(d, scratch);
+        }
     } else if (d.nch == 8) {
         if (pair) launch_dw<1, 8, 2>(d, scratch, dim3(bx), s); else launch_dw<1, 8, 1>(d, scratch, dim3(bx), s);
     } else if (d.nch == 16) {
