@@ -506,9 +506,9 @@ int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
     TRON_CUDA(cudaGetLastError());
     /* spokes in pairs when consecutive spokes are neighbours in angle (linear order) */
     const int pair_env = getenv("TRON_DEGRID_PAIR") ? atoi(getenv("TRON_DEGRID_PAIR")) : -1;
-    /* (8- and 16-channel shards: measured slower in pairs, 2.81 -> 3.02 ms for cfg5's 8-coil shard -- their requests are
-     * 64 / 128 bytes and the second spoke's registers cost a block per SM) */
-    const bool pair = pair_env >= 0 ? pair_env != 0 : (d.pair_spokes != 0 && d.nch >= 32);
+    /* (from 16 channels on: the 16-coil cfg5 shard 4.01 -> 3.77 ms; the 8-channel ROW kernel was slower in pairs,
+     * 2.81 -> 3.02 ms -- 8 channels have their own kernel below) */
+    const bool pair = pair_env >= 0 ? pair_env != 0 : (d.pair_spokes != 0 && d.nch >= 16);
     const int P = pair ? 2 : 1;
     const long long nwork = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 8 * P - 1) / (8 * P));
     int bx = (int)(nwork < 148 * 32 ? nwork : 148 * 32);
