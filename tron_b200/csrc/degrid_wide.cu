@@ -299,26 +299,34 @@ template <int P> struct __align__(16) Dw8Weights {
     float4 wx[P][DW_MAXU];   /* row factor of samples 0..3 of spoke p */
     float4 wy[P][32];        /* column factor, zero past the window */
     float4 wp[P][32];        /* wx[row] * wy[column] of the row in flight */
-    int coffT[32];           /* wrapped column indices, [step of 16][quarter-warp][quad]: one 16-byte load per lane */
+    int coffT[32];           /* wrapped column indices, [step][sub-warp][quad]: one 16-byte load per lane */
 };
 
-/* P = spokes per warp: with linear angle order the neighbours pe, pe + 1 share a window (see degrid_wide_kernel), a
- * loaded cell and the row's bookkeeping then serve 8 samples -- this kernel is bound by issued instructions, not by
- * L1.  A pair whose union window does not fit is walked spoke by spoke. */
-template <bool HALF, int P>
-__global__ void __launch_bounds__(256)
-degrid_wide8_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interleaved grid, 8 channels */)
+/* CPL = lanes per cell: 8 (8 channels, four quarter-warps on four adjacent columns) or 16 with NCHUNK = 2 (32
+ * channels, a lane holds two adjacent ones, the half-warps on two adjacent columns: cfg5's shards on 2 GPUs -- with a
+ * whole warp per cell and one channel per lane a cell cost 2 + 4 wavefronts for 8 FFMA2, here a pair of cells costs
+ * 4 + 2 for 32).
+ * P = spokes per warp: with linear angle order the neighbours pe, pe + 1 share a window (see degrid_wide_kernel), a
+ * loaded cell and the row's bookkeeping then serve 8 samples.  A pair whose union window does not fit is walked
+ * spoke by spoke. */
+template <bool HALF, int P, int CPL, int NCHUNK>
+__global__ void __launch_bounds__(256, 2)
+degrid_cols_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* interleaved grid */)
 {
     constexpr int NS = P * DW_S;
+    constexpr int NSUB = 32 / CPL;                       /* sub-warps = adjacent columns taken together */
+    constexpr int STEPC = 4 * NSUB;                      /* columns per step: four quads in flight */
     __shared__ Dw8Weights<P> sw8[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Dw8Weights<P> &S = sw8[warp];
-    const int n = d.n;
+    const int n = d.n, nch = d.nch;
     const int groups_per_spoke = (d.nro + DW_S - 1) / DW_S;
     const float W = d.kb.W;
     const float c0 = (float)((n + 1) / 2);
     const float inv_nro = rcp_approx((float)d.nro);
-    const int clane = lane & 7, rsub = lane >> 3;        /* channel, quarter-warp = column inside a quad of columns */
+    const int clane = lane % CPL, rsub = lane / CPL;     /* channel lane, sub-warp = column inside a quad of columns */
+    const int chan0 = blockIdx.y * CPL * NCHUNK;
+    const unsigned cstride = (unsigned)nch * (unsigned)sizeof(float2);   /* bytes between neighbouring columns */
     const long long nwork = (long long)((d.npe + 8 * P - 1) / (8 * P)) * groups_per_spoke;
     for (long long wb = blockIdx.x; wb < nwork; wb += gridDim.x) {
         const int pe0 = ((int)(wb / groups_per_spoke) * 8 + warp) * P;
@@ -351,9 +359,11 @@ degrid_wide8_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* inter
             for (int p = 1; p < P; ++p) { x0 = min(x0, bx0[p]); x1 = max(x1, bx1[p]); y0 = min(y0, by0[p]); y1 = max(y1, by1[p]); }
             if (x1 - x0 + 1 > DW_MAXU || y1 - y0 + 1 > DW_MAXU) npass = P;
         }
-        float2 acc[NS];
+        float2 acc[NCHUNK][NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) acc[k] = make_float2(0.f, 0.f);
+        for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+            for (int k = 0; k < NS; ++k) acc[c][k] = make_float2(0.f, 0.f);
 
         for (int pass = 0; pass < npass; ++pass) {
             int xlo = 1 << 30, xhi = -(1 << 30), ylo = 1 << 30, yhi = -(1 << 30);
@@ -364,7 +374,8 @@ degrid_wide8_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* inter
                 }
             if (xhi < xlo) continue;                                            /* (a spoke past the last one) */
             const int nux = min(xhi - xlo + 1, DW_MAXU), nuy = min(yhi - ylo + 1, DW_MAXU);
-            const int nuyP = (nuy + 15) & ~15;                                  /* 16 or 32 columns */
+            const int nsteps = (nuy + STEPC - 1) / STEPC;                       /* <= 32 / STEPC */
+            const int nuyP = nsteps * STEPC;
 
             /* phase A: lanes = rows, then columns */
             __syncwarp();
@@ -388,32 +399,30 @@ degrid_wide8_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* inter
                     if (isrow) S.wx[p][i] = make_float4(w4[0], w4[1], w4[2], w4[3]);
                     else S.wy[p][c] = make_float4(w4[0], w4[1], w4[2], w4[3]);
                 }
-                /* column c = 16 step + 4 quad + quarter-warp: stored as [step][quarter-warp][quad] */
-                if (!isrow) S.coffT[(c & ~15) + (c & 3) * 4 + ((c >> 2) & 3)] = wrap_cell_w(u, n);   /* periodic, tron.cu:570 */
+                /* column c = STEPC step + NSUB quad + sub-warp: stored as [step][sub-warp][quad] */
+                if (!isrow) S.coffT[(c / STEPC) * STEPC + (c % NSUB) * 4 + ((c / NSUB) & 3)] = wrap_cell_w(u, n);   /* periodic, tron.cu:570 */
             }
             __syncwarp();
 
-            /* phase B: lanes = (quarter-warp = column of a quad, channel) */
-            const int sh = nuyP >> 5;                                           /* steps per row: 1 << sh */
-            const int nq = nux << sh;
-            auto load = [&](float2 (&v)[4], int q) {
-                const int i0 = q >> sh, st = q & ((1 << sh) - 1);
-                const int row = wrap_cell_w(xlo + i0, n);                       /* periodic, tron.cu:569 */
-                const char *base = (const char *)(gi + ((size_t)row * n) * 8 + clane);
-                const int4 co = *reinterpret_cast<const int4 *>(&S.coffT[st * 16 + rsub * 4]);
-                v[0] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.x * 64u));
-                v[1] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.y * 64u));
-                v[2] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.z * 64u));
-                v[3] = ldg2v((const float2 *)(base + (unsigned long long)(unsigned)co.w * 64u));
+            /* phase B: lanes = (sub-warp = column of a quad, channel); the loads run one step ahead, across rows */
+            int li = 0, ls = 0, fi = 0, fs = 0;                                 /* (row, step) cursors of loads and FMAs */
+            auto load = [&](float2 (&v)[4][NCHUNK]) {
+                const int row = wrap_cell_w(xlo + li, n);                       /* periodic, tron.cu:569 */
+                const char *base = (const char *)(gi + ((size_t)row * n) * nch + chan0 + clane * NCHUNK);
+                const int4 co = *reinterpret_cast<const int4 *>(&S.coffT[ls * STEPC + rsub * 4]);
+                ldg_cell<NCHUNK>(v[0], base + (unsigned long long)(unsigned)co.x * cstride);
+                ldg_cell<NCHUNK>(v[1], base + (unsigned long long)(unsigned)co.y * cstride);
+                ldg_cell<NCHUNK>(v[2], base + (unsigned long long)(unsigned)co.z * cstride);
+                ldg_cell<NCHUNK>(v[3], base + (unsigned long long)(unsigned)co.w * cstride);
+                if (++ls == nsteps) { ls = 0; ++li; }
             };
-            auto fma = [&](const float2 (&v)[4], int q) {
-                const int i0 = q >> sh, st = q & ((1 << sh) - 1);
-                if (st == 0) {                                                  /* a new row: its tap weights */
+            auto fma = [&](const float2 (&v)[4][NCHUNK]) {
+                if (fs == 0) {                                                  /* a new row: its tap weights */
                     __syncwarp();
                     if (lane < nuyP) {
 #pragma unroll
                         for (int p = 0; p < P; ++p) {
-                            const float4 a = S.wx[p][i0], b = S.wy[p][lane];
+                            const float4 a = S.wx[p][fi], b = S.wy[p][lane];
                             S.wp[p][lane] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
                         }
                     }
@@ -423,40 +432,55 @@ degrid_wide8_kernel(const DegridLaunch d, const float2 *__restrict__ gi /* inter
                 for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
-                        const float4 b = S.wp[p][st * 16 + 4 * jj + rsub];
-                        ffma2d(acc[4 * p + 0], b.x, v[jj]); ffma2d(acc[4 * p + 1], b.y, v[jj]);
-                        ffma2d(acc[4 * p + 2], b.z, v[jj]); ffma2d(acc[4 * p + 3], b.w, v[jj]);
+                        const float4 b = S.wp[p][fs * STEPC + NSUB * jj + rsub];
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c) {
+                            ffma2d(acc[c][4 * p + 0], b.x, v[jj][c]); ffma2d(acc[c][4 * p + 1], b.y, v[jj][c]);
+                            ffma2d(acc[c][4 * p + 2], b.z, v[jj][c]); ffma2d(acc[c][4 * p + 3], b.w, v[jj][c]);
+                        }
                     }
+                if (++fs == nsteps) { fs = 0; ++fi; }
             };
-            float2 va[4], vb[4];
-            load(va, 0);
+            const int nq = nux * nsteps;
+            float2 va[4][NCHUNK], vb[4][NCHUNK];
+            load(va);
             for (int q = 0; q < nq; q += 2) {
-                if (q + 1 < nq) load(vb, q + 1);
-                fma(va, q);
+                if (q + 1 < nq) load(vb);
+                fma(va);
                 if (q + 1 >= nq) break;
-                if (q + 2 < nq) load(va, q + 2);
-                fma(vb, q + 1);
+                if (q + 2 < nq) load(va);
+                fma(vb);
             }
         }
-        /* add the quarter-warps' partial sums */
+        /* add the sub-warps' partial sums */
 #pragma unroll
-        for (int k = 0; k < NS; ++k)
+        for (int c = 0; c < NCHUNK; ++c)
 #pragma unroll
-            for (int o = 8; o < 32; o <<= 1) {
-                acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
-                acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
-            }
-        if (rsub == 0) {
+            for (int k = 0; k < NS; ++k)
+#pragma unroll
+                for (int o = CPL; o < 32; o <<= 1) {
+                    acc[c][k].x += __shfl_xor_sync(0xffffffffu, acc[c][k].x, o);
+                    acc[c][k].y += __shfl_xor_sync(0xffffffffu, acc[c][k].y, o);
+                }
+        if (rsub == 0 && chan0 + clane * NCHUNK < nch) {
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 const int pe = pe0 + k / DW_S, ro = ro0 + k % DW_S;
                 if (ro >= d.nro || pe >= d.npe) continue;
-                const size_t o = ((size_t)pe * d.nro + ro) * d.nc_total + d.ch0 + clane;
-                if (HALF) ((__half2 *)d.samples)[o] = __float22half2_rn(acc[k]);
-                else ((float2 *)d.samples)[o] = acc[k];
+                const size_t base = ((size_t)pe * d.nro + ro) * d.nc_total + d.ch0 + chan0 + clane * NCHUNK;
+                store_chan<NCHUNK, HALF, NS>(d.samples, base, acc, k);
             }
         }
     }
+}
+
+template <int P, int CPL, int NCHUNK>
+static void launch_cols(const DegridLaunch &d, const float2 *scratch, cudaStream_t s)
+{
+    const long long nw = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 8 * P - 1) / (8 * P));
+    dim3 grid((unsigned)(nw < 148 * 32 ? nw : 148 * 32), (unsigned)(d.nch / (CPL * NCHUNK)));
+    if (d.half_out) degrid_cols_kernel<true, P, CPL, NCHUNK><<<grid, 256, 0, s>>>(d, scratch);
+    else            degrid_cols_kernel<false, P, CPL, NCHUNK><<<grid, 256, 0, s>>>(d, scratch);
 }
 
 /* planar [ch][cell] -> interleaved [cell][ch], 32 x 32 tiles through shared memory */
@@ -512,18 +536,14 @@ int launch_degrid_wide(const DegridLaunch &d, float2 *scratch, cudaStream_t s)
     const int P = pair ? 2 : 1;
     const long long nwork = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + 8 * P - 1) / (8 * P));
     int bx = (int)(nwork < 148 * 32 ? nwork : 148 * 32);
+    const bool even2 = d.nc_total % 2 == 0 && d.ch0 % 2 == 0 && ((uintptr_t)d.samples) % 16 == 0;
     if (d.nch == 8 && getenv("TRON_DEGRID_ROWS8") == nullptr) {
         /* (the column kernel pairs spokes whenever the angle order is linear: it is bound by instructions, not L1) */
         const bool pair8 = pair_env >= 0 ? pair_env != 0 : d.pair_spokes != 0;
-        const long long nw8 = (long long)((d.nro + DW_S - 1) / DW_S) * ((d.npe + (pair8 ? 16 : 8) - 1) / (pair8 ? 16 : 8));
-        const int b8 = (int)(nw8 < 148 * 32 ? nw8 : 148 * 32);
-        if (pair8) {
-            if (d.half_out) degrid_wide8_kernel<true, 2><<<b8, 256, 0, s>>>(d, scratch);
-            else            degrid_wide8_kernel<false, 2><<<b8, 256, 0, s>>>(d, scratch);
-        } else {
-            if (d.half_out) degrid_wide8_kernel<true, 1><<<b8, 256, 0, s>>>(d, scratch);
-            else            degrid_wide8_kernel<false, 1><<<b8, 256, 0, s>>>(d, scratch);
-        }
+        if (pair8) launch_cols<2, 8, 1>(d, scratch, s); else launch_cols<1, 8, 1>(d, scratch, s);
+    } else if (d.nch == 32 && even2 && getenv("TRON_DEGRID_ROWS32") == nullptr) {
+        /* 32 channels (cfg5's shards on 2 GPUs): half-warps on adjacent columns, two channels per lane */
+        if (pair) launch_cols<2, 16, 2>(d, scratch, s); else launch_cols<1, 16, 2>(d, scratch, s);
     } else if (d.nch == 8) {
         if (pair) launch_dw<1, 8, 2>(d, scratch, dim3(bx), s); else launch_dw<1, 8, 1>(d, scratch, dim3(bx), s);
     } else if (d.nch == 16) {
