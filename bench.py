@@ -656,16 +656,39 @@ def run_ours(args):
     build.build()
     rank, world, local = dist_setup(args.gpus)
     dims, flags, desc = WORKLOADS[args.workload]
-    t_plan0 = time.perf_counter()
     cfg = t.make_config(dims, device=local, **flags)
-    plan = t.Plan(cfg)
-    plan_create_ms = (time.perf_counter() - t_plan0) * 1e3
-    g = plan.geom.as_dict()
+    g = t.geometry(cfg).as_dict()                                   # host-only (tron_geometry_compute)
     nsamp = g["nc"] * g["nro"] * g["npe1work"] * g["nz"]            # coil-samples gridded per step
     in_elems, out_elems = g["shard_in_elems"], g["shard_out_elems"]
     d_in, h_in = make_input(torch, in_elems, rank)
-    d_out = torch.zeros(out_elems * 2, dtype=torch.float32, device="cuda")
     h_out = torch.zeros(out_elems * 2, dtype=torch.float32, pin_memory=True)
+
+    # ---- cold span, measured FIRST: what the reference's recon_radial2d brackets (tron.cu:726-786: init, buffers,
+    # recon, shutdown) through the same-named legacy symbol = plan create + recon + destroy per call.  First because
+    # the span is mostly cudaMalloc / cudaFree, whose cost grows with what the process already holds (with this
+    # bench's 19 GB of work buffers and torch's cache alive: 50 instead of 23 ms) and with the reference's library
+    # mapped by the parity checker further down (its own CUDA runtime, cuFFT, cuBLAS: ~5x, profiles/r02_cold_span.txt)
+    cold_leg = None
+    if world == 1 and not args.lean and args.workload == "cfg2":
+        L = t.load_library()
+        assert L.tron_set_config(C.byref(cfg)) == 0
+        cold = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            L.recon_radial2d(C.c_void_p(h_out.data_ptr()), C.c_void_p(h_in.data_ptr()))
+            cold.append((time.perf_counter() - t0) * 1e3)
+        med = float(np.median(cold[1:]))
+        cold_leg = {"ms_per_step": med, "value": nsamp / (med * 1e-3), "unit": "samples/s", "runs_ms": cold,
+                    "how": "legacy recon_radial2d(h_out, h_in): tron_plan_create + tron_recon_host + tron_plan_destroy per "
+                           "call, CUDA context already up (as in the reference arm); median of the last 3 of 4 calls (the "
+                           "first loads the kernels, like the reference arm's warm-up step)"}
+
+    t_plan0 = time.perf_counter()
+    plan = t.Plan(cfg)
+    plan_create_ms = (time.perf_counter() - t_plan0) * 1e3
+    g = plan.geom.as_dict()
+    d_out = torch.zeros(out_elems * 2, dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- device-resident throughput
@@ -708,22 +731,9 @@ def run_ours(args):
     extras = {}
     if not args.lean and args.workload == "cfg2":
         if world == 1:
-            # cold span FIRST (before the checker below maps the reference's library -- its own CUDA runtime, cuFFT,
-            # cuBLAS -- into this process: with it loaded every cudaMalloc/cudaFree here is ~5x slower,
-            # profiles/r02_cold_span.txt): what the reference's recon_radial2d brackets (tron.cu:726-786: init, buffers, recon,
-            # shutdown) through the same-named legacy symbol = plan create + recon + destroy per call
-            L = t.load_library()
-            assert L.tron_set_config(C.byref(cfg)) == 0
-            cold = []
-            for _ in range(3):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                L.recon_radial2d(C.c_void_p(h_out.data_ptr()), C.c_void_p(h_in.data_ptr()))
-                cold.append((time.perf_counter() - t0) * 1e3)
-            extras["e2e_cold"] = {"ms_per_step": float(np.median(cold)), "value": nsamp / (float(np.median(cold)) * 1e-3),
-                                  "unit": "samples/s", "runs_ms": cold, "plan_create_ms_first": plan_create_ms,
-                                  "how": "legacy recon_radial2d(h_out, h_in): tron_plan_create + tron_recon_host + "
-                                         "tron_plan_destroy per call, CUDA context already up (as in the reference arm)"}
+            if cold_leg is not None:
+                cold_leg["plan_create_ms_first"] = plan_create_ms
+                extras["e2e_cold"] = cold_leg
             # parity of THIS run's output against the unmodified reference (checker, untimed)
             extras["parity"] = parity_vs_reference(torch, d_out, d_in, dims, flags, g, [0, 1, 31, 32, 477, 954, 955])
         if world == 1:
