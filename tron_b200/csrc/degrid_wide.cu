@@ -1,10 +1,11 @@
 /*
- * degrid_wide.cu -- degridding for many receive channels (nc a multiple of 32): lanes = channels.
+ * degrid_wide.cu -- degridding for many receive channels (nc a multiple of 32, or 8 / 16 at wide
+ * kernels): lanes = channels.
  *
  * Same operator and tap set as degrid.cu (reference: degridradial2d,
- * /root/reference/src/tron.cu:540-577).  A warp owns four consecutive samples of one spoke; their
- * tap windows overlap almost completely (neighbouring samples are one cell apart), so the warp
- * walks the union window once:
+ * /root/reference/src/tron.cu:540-577).  A warp owns four consecutive samples of one spoke -- of
+ * two neighbouring spokes when the angle order is linear -- whose tap windows overlap almost
+ * completely (neighbouring samples are one cell apart), so the warp walks the union window once:
  *
  *   A  lanes = rows / columns of the union window: the Kaiser-Bessel factor of every row and
  *      every column for each of the four samples (zero outside that sample's own support, decided
@@ -16,6 +17,11 @@
  * With -k 6 (13 x 13 taps) this is FP32 bound; the point of the blocking is
  * that a cell costs one load + four FMAs instead of four loads + four FMAs, all requests are full
  * lines, and the per-tap weight work is amortised over the channels.
+ *
+ * Two kernels: degrid_wide_kernel (a warp, or 2 / 4 sub-warps on different ROWS, per cell: 64 and 16
+ * channels) and degrid_cols_kernel (sub-warps on adjacent COLUMNS of one row: 8 and 32 channels).
+ * Both are bound by L1 wavefronts per FFMA2, which is what the blocking is chosen by (DESIGN.md
+ * section 3.3).
  *
  * Input grid: channel-interleaved g[(row*n + col)*nch + ch] (fwd FFT output transposed by
  * planar_to_interleaved_kernel); output: samples[(pe*nro + ro)*nc_total + ch0 + ch].

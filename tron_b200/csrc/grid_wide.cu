@@ -18,9 +18,14 @@
  *
  * The list is drained whenever it could overflow, so blocks near DC (thousands of taps) need no
  * special path.  Sliding golden-angle windows share phase A across GS = 4 slices like grid.cu.
- * nc = 16 runs two entries per iteration (one per half-warp) and folds the halves at the end;
- * nc = 64 keeps two channels per lane.  Output: planar grid[slice][ch][row][col]; a lane writes
- * whole 32-byte sectors (4 cells of a row) of its channel plane.
+ * nc = 16 / 8 (coil shards at wide kernels) run two / four entries per step on sub-warps and fold
+ * them at the end; nc = 64 gives a lane two ADJACENT channels (one request per sample).
+ * Output: planar grid[slice][ch][row][col]; the CTA's eight blocks tile 16 x 4 cells and are
+ * transposed through shared memory, so a channel's rows leave as 128 contiguous bytes.
+ *
+ * What bounds it (ncu, profiles/r02_ncu_cfg3_grid_wide_v2.txt): the L1 data pipe -- an entry is
+ * 4 wavefronts for its weights (a broadcast LDS.128 costs two) + 2 for the sample per 8 FFMA2 --
+ * not the instruction count.
  */
 #include "tron_internal.h"
 #include <stdlib.h>
